@@ -1,0 +1,123 @@
+"""ctypes binding of libf16_b200.so (C ABI declared in include/f16.h) + the in-tree nvcc build.
+
+There is NO CPU fallback: if the shared library is missing or a call fails, an exception is
+raised.  PyTorch tensors are used purely as device-memory containers (``.data_ptr()``).
+"""
+
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libf16_b200.so")
+
+# (source, extra flags).  -fmad=false wherever float64 expressions must round like the CPU.
+_SOURCES = (
+    ("f16_tree.cu", ["-fmad=false"]),
+    ("f16_misc.cu", ["-fmad=false"]),
+    ("f16_sort.cu", []),
+    ("f16_knn.cu", []),
+)
+_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(a, b):
+    return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
+
+
+def build(force=False, verbose=False):
+    """Compiles every CUDA source for sm_100a and links libf16_b200.so in-tree."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    hdrs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    objs, rebuilt = [], False
+    procs = []
+    for src, extra in _SOURCES:
+        s = os.path.join(_CSRC, src)
+        o = os.path.join(_CSRC, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs):
+            cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *_ARCH, "-Xcompiler", "-fPIC",
+                   "-Xptxas", "-v" if verbose else "-O3", *extra, "-c", s, "-o", o]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+            rebuilt = True
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, out.decode()))
+        if verbose:
+            sys.stderr.write(out.decode())
+    if rebuilt or not os.path.exists(LIB_PATH):
+        cmd = [nvcc, "-shared", *_ARCH, "-o", LIB_PATH, *objs, "-lcudart"]
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+c_void_p, c_int, c_int32, c_int64, c_uint32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
+                                               ctypes.c_int64, ctypes.c_uint32)
+
+# name -> argtypes ; every symbol include/f16.h declares (tests check the export list)
+SIGNATURES = {
+    "f16_last_error": ([], ctypes.c_char_p),
+    "f16_version": ([], c_int),
+    "f16_init": ([c_int], c_int),
+    "f16_gather_rows_f32": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "f16_gather_rows_f64": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "f16_gather_u8": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "f16_argsort_columns": ([c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
+    "f16_tree_seeds": ([c_uint32, c_int32, c_int32, c_void_p, c_void_p], c_int),
+    "f16_bootstrap_counts": ([c_void_p, c_int32, c_int64, c_void_p, c_void_p], c_int),
+    "f16_forest_fit": ([c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                        c_uint32, c_void_p, ctypes.POINTER(c_void_p)], c_int),
+    "f16_forest_predict": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "f16_forest_status": ([c_void_p, c_void_p], c_int),
+    "f16_forest_n_trees": ([c_void_p], c_int),
+    "f16_forest_node_counts": ([c_void_p, c_void_p, c_void_p], c_int),
+    "f16_forest_export": ([c_void_p, c_int32, c_int64] + [c_void_p] * 8 + [c_void_p], c_int),
+    "f16_forest_free": ([c_void_p, c_void_p], None),
+    "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p], c_int),
+    "f16_smote_generate": ([c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
+                            c_void_p, c_void_p], c_int),
+    "f16_tomek_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
+    "f16_enn_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
+    "f16_compact_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p], c_int),
+    "f16_confusion": ([c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
+}
+
+
+class F16Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library (never builds silently, never falls back to a CPU path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise F16Error("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is mandatory; there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise F16Error("libf16_b200 error %d: %s" % (rc, lib().f16_last_error().decode()))
+
+
+_inited = set()
+
+
+def init(device=0):
+    if device not in _inited:
+        check(lib().f16_init(int(device)))
+        _inited.add(device)

@@ -1,0 +1,120 @@
+/* f16.h - C ABI of libf16_b200.so: the B200 (sm_100a) implementation of the `scores`
+ * hot path of flake-it/flake16-framework.
+ *
+ * The reference has no FFI of its own: the path is Python calling scikit-learn /
+ * imbalanced-learn estimators (experiment.py:73-100 construct them, :446-490 use them).
+ * Each entry point below therefore names the reference call site (experiment.py:line) and the
+ * third-party routine whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 or a negative F16_ERR_* code and never throws;
+ * f16_last_error() gives the thread-local message.  All *_dev pointers are device pointers
+ * owned by the caller (any allocator; the Python layer uses torch tensors as containers).
+ * Every call takes an explicit CUDA stream (cudaStream_t passed as void*) and is asynchronous
+ * with respect to the host unless noted "synchronises".  Scratch memory is taken from the CUDA
+ * stream-ordered pool (cudaMallocAsync) on that stream.  Opaque handles are freed only by their
+ * *_free.  No global RNG state: seeds are arguments, mirroring the reference's
+ * `random_state=0` re-seeding on every fit / fit_resample.
+ */
+#ifndef F16_H
+#define F16_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F16_OK 0
+#define F16_ERR_INVALID (-1)
+#define F16_ERR_CUDA (-2)
+#define F16_ERR_OVERFLOW (-3)
+#define F16_ERR_NOMEM (-4)
+
+#define F16_KIND_DT 0 /* DecisionTreeClassifier(random_state=seed)   experiment.py:98 */
+#define F16_KIND_RF 1 /* RandomForestClassifier(random_state=seed)   experiment.py:97 */
+#define F16_KIND_ET 2 /* ExtraTreesClassifier(random_state=seed)     experiment.py:96 */
+
+typedef struct f16_forest f16_forest;
+
+const char* f16_last_error(void);
+int f16_version(void);
+/* Selects the device and keeps the stream-ordered memory pool from trimming. */
+int f16_init(int device);
+
+/* ---- data staging ------------------------------------------------------------------
+ * features[train] / features[test] (experiment.py:459-460) fused with the float32 cast that
+ * sklearn applies in BaseForest.fit / predict.  X_dev: float64 [N][d] row-major; idx_dev: int64
+ * row indices or NULL (identity); out: float32 [n_out][dp], dp = 8 if d <= 8 else 16, zero
+ * padded - the row layout every tree kernel expects. */
+int f16_gather_rows_f32(const double* X_dev, int32_t d, const int64_t* idx_dev, int64_t n_out,
+                        float* out_dev, void* stream);
+int f16_gather_rows_f64(const double* X_dev, int32_t d, const int64_t* idx_dev, int64_t n_out,
+                        double* out_dev, void* stream);
+int f16_gather_u8(const uint8_t* y_dev, const int64_t* idx_dev, int64_t n_out, uint8_t* out_dev, void* stream);
+
+/* ---- tree ensembles -------------------------------------------------------------------
+ * Per-column argsort of a float32 row matrix ([n][dp]); sorted_idx_dev: int32 [d][n].
+ * Replaces the per-node sort of sklearn's BestSplitter (tree/_partitioner.pyx:59-109). */
+int f16_argsort_columns(const float* X_dev, int64_t n, int32_t d, int32_t* sorted_idx_dev, void* stream);
+
+/* Host-only: per-tree seeds exactly as sklearn derives them from random_state=seed
+ * (ensemble/_base.py:_set_random_states, tree/_splitter.pyx:155).  Arrays of n_trees. */
+int f16_tree_seeds(uint32_t seed, int32_t kind, int32_t n_trees, uint32_t* tree_seed, uint32_t* rand_r_state);
+
+/* RandomForest bootstrap: MT19937(tree_seed[t]).randint(0, n, n) -> bincount
+ * (ensemble/_forest.py:94-112,150-156).  w_dev: uint8 [n_trees][(n+3)/4*4]. */
+int f16_bootstrap_counts(const uint32_t* tree_seed_host, int32_t n_trees, int64_t n, uint8_t* w_dev, void* stream);
+
+/* model.fit(features_train, labels_train)  (experiment.py:469).
+ * X_dev float32 [n][dp] (from f16_gather_rows_f32), y_dev uint8 class index 0/1,
+ * sorted_idx_dev from f16_argsort_columns (required for DT/RF, may be NULL for ET).
+ * n_estimators is ignored for F16_KIND_DT.  max_features: sklearn's resolved value
+ * (int(sqrt(d)) for the forests, d for the single tree). */
+int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
+                   const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
+                   int32_t max_features, uint32_t seed, void* stream, f16_forest** out);
+/* model.predict(features_test)  (experiment.py:473): pred_dev uint8 [n] class index. */
+int f16_forest_predict(const f16_forest* forest, const float* X_dev, int64_t n, uint8_t* pred_dev, void* stream);
+/* Synchronises the stream; returns the device-side status of the fit (0 = ok). */
+int f16_forest_status(const f16_forest* forest, void* stream);
+int f16_forest_n_trees(const f16_forest* forest);
+/* Synchronises. counts_host: int32 [n_trees]. */
+int f16_forest_node_counts(const f16_forest* forest, int32_t* counts_host, void* stream);
+/* Synchronises. One tree in sklearn's tree_ layout (children_left/right, feature, threshold,
+ * impurity, n_node_samples, weighted_n_node_samples, value[n_nodes][2]) for parity tests. */
+int f16_forest_export(const f16_forest* forest, int32_t tree, int64_t n_nodes, int64_t* left, int64_t* right,
+                      int64_t* feature, double* threshold, double* impurity, int64_t* n_node_samples,
+                      double* weighted_n_node_samples, double* value, void* stream);
+void f16_forest_free(f16_forest* forest, void* stream);
+
+/* ---- balancing: balancing.fit_resample(features_train, labels_train)  (experiment.py:463-466)
+ * Exact float64 brute-force k-NN (NearestNeighbors(k).fit(A).kneighbors(Q)); idx_dev int32
+ * [nq][k], ordered by (distance, index).  k <= 8, d <= 16. */
+int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, int32_t k,
+            int32_t* idx_dev, void* stream);
+/* SMOTE._make_samples: X_new[j] = C[row] + steps[j] * (C[nn[row][1 + col]] - C[row]) with
+ * row = sample_idx[j] / k, col = sample_idx[j] % k; nn_dev int32 [n_min][k + 1] from f16_knn. */
+int f16_smote_generate(const double* C_dev, int64_t n_min, int32_t d, const int32_t* nn_dev, int32_t k,
+                       const int64_t* sample_idx_dev, const double* steps_dev, int64_t n_new,
+                       double* Xnew_dev, void* stream);
+/* TomekLinks.is_tomek / EditedNearestNeighbours(kind_sel="all") decisions.  nn_dev int32 [n][kk]
+ * (column 0 = the row itself), clean_mask bit c set <=> class c is cleaned; keep_dev uint8 [n]. */
+int f16_tomek_keep(const int32_t* nn_dev, int32_t kk, const uint8_t* y_dev, int64_t n, int32_t clean_mask,
+                   uint8_t* keep_dev, void* stream);
+int f16_enn_keep(const int32_t* nn_dev, int32_t kk, const uint8_t* y_dev, int64_t n, int32_t clean_mask,
+                 uint8_t* keep_dev, void* stream);
+/* Row compaction: grouped = 0 keeps the original order (TomekLinks), 1 = class-0 rows then
+ * class-1 rows (ENN).  src_index_dev (int64 [n], optional) receives the source row of each
+ * output row; n_out_dev int64[2] = {rows kept, class-0 rows kept}. */
+int f16_compact_rows(const double* X_dev, const uint8_t* y_dev, const uint8_t* keep_dev, int64_t n, int32_t d,
+                     int32_t grouped, double* Xout_dev, uint8_t* yout_dev, int64_t* src_index_dev,
+                     int64_t* n_out_dev, void* stream);
+
+/* ---- scoring: the per-row loop of experiment.py:476-483.  counts_dev int64 [n_proj + 1][3]
+ * (FP, FN, TP per project, last row = total), accumulated across calls (folds). */
+int f16_confusion(const uint8_t* y_dev, const uint8_t* pred_dev, const int32_t* proj_dev, int64_t n,
+                  int32_t n_proj, int64_t* counts_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

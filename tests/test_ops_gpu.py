@@ -1,0 +1,101 @@
+"""GPU parity of the supporting operators (RNG, sort, k-NN, samplers, confusion) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from util import make_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bootstrap_counts_match_numpy(cuda):
+    """sklearn/ensemble/_forest.py:94-112: RandomState(seed).randint(0, n, n) -> bincount."""
+    from flake16_framework_b200 import ops
+    for n in (1, 2, 5, 624, 1000, 4096, 90001):
+        seeds, _ = ops.tree_seeds(0, ops.KIND_RF, 4)
+        w = ops.bootstrap_counts(seeds, n).cpu().numpy()
+        for t, s in enumerate(seeds):
+            ref = np.bincount(np.random.RandomState(int(s)).randint(0, n, n), minlength=n)
+            assert np.array_equal(w[t], ref), (n, t)
+
+
+def test_argsort_columns(cuda):
+    from flake16_framework_b200 import ops
+    rs = np.random.RandomState(0)
+    for n, d in ((1, 3), (7, 16), (5000, 7), (70001, 16)):
+        X = rs.randn(n, d)
+        X[:, 0] = rs.randint(0, 5, n)            # heavy ties
+        if d > 2:
+            X[:, 2] = -np.abs(X[:, 2])           # negatives
+        Xd = torch.from_numpy(X).cuda()
+        rows = ops.rows_f32(Xd)
+        idx = ops.argsort_columns(rows, d).cpu().numpy()
+        X32 = X.astype(np.float32)
+        for f in range(d):
+            assert np.array_equal(np.sort(idx[f]), np.arange(n)), (n, d, f)
+            v = X32[idx[f], f]
+            assert np.all(v[1:] >= v[:-1]), (n, d, f)
+
+
+def test_rows_f32_gather(cuda):
+    from flake16_framework_b200 import ops
+    rs = np.random.RandomState(1)
+    for d in (7, 16):
+        X = rs.randn(100, d) * 1e3
+        idx = rs.randint(0, 100, 37)
+        r = ops.rows_f32(torch.from_numpy(X).cuda(), torch.from_numpy(idx).cuda()).cpu().numpy()
+        assert r.shape[1] == (8 if d == 7 else 16)
+        assert np.array_equal(r[:, :d], X[idx].astype(np.float32))
+        assert np.all(r[:, d:] == 0)
+
+
+@pytest.mark.parametrize("cfg", [dict(n=3000, fset="Flake16", prep="None"), dict(n=3000, fset="Flake16", prep="Scaling"),
+                                 dict(n=3000, fset="FlakeFlagger", prep="PCA"), dict(n=20000, fset="Flake16", prep="PCA")])
+def test_knn_matches_sklearn(cuda, cfg):
+    from sklearn.neighbors import NearestNeighbors
+    from flake16_framework_b200 import ops
+    X, _, _ = make_dataset(**cfg)
+    Xd = torch.from_numpy(X).cuda()
+    for k in (2, 4, 6):
+        ours = ops.knn(Xd, Xd, k).cpu().numpy()
+        ref = NearestNeighbors(n_neighbors=k).fit(X).kneighbors(X, return_distance=False)
+        frac = (ours == ref).all(axis=1).mean()
+        assert frac == 1.0, "k=%d: %.6f of rows have identical neighbour lists" % (k, frac)
+
+
+SAMPLERS = ["TomekLinks", "SMOTE", "EditedNearestNeighbours", "SMOTEENN", "SMOTETomek"]
+
+
+@pytest.mark.parametrize("name", SAMPLERS)
+@pytest.mark.parametrize("cfg", [dict(n=4000, fset="Flake16", prep="None"), dict(n=4000, fset="FlakeFlagger", prep="Scaling"),
+                                 dict(n=6000, fset="Flake16", prep="PCA", flaky="OD")])
+def test_samplers_match_oracle(cuda, name, cfg):
+    import samplers_np as O
+    from flake16_framework_b200 import estimators as E
+    X, y, _ = make_dataset(**cfg)
+    kw = {"random_state": 0} if "SMOTE" in name else {}
+    Xr, yr = getattr(O, name)(**kw).fit_resample(X, y)
+    Xo, yo = getattr(E, name)(**kw).fit_resample(X, y)
+    assert Xo.shape == Xr.shape, (Xo.shape, Xr.shape)
+    assert np.array_equal(yo, yr)
+    assert np.array_equal(Xo.view(np.int64), Xr.view(np.int64)), "resampled rows differ bitwise"
+
+
+def test_confusion(cuda):
+    from flake16_framework_b200 import ops
+    rs = np.random.RandomState(5)
+    n, n_proj = 100000, 26
+    y = (rs.rand(n) < 0.1).astype(np.uint8)
+    p = (rs.rand(n) < 0.1).astype(np.uint8)
+    proj = rs.randint(0, n_proj, n).astype(np.int32)
+    counts = torch.zeros((n_proj + 1, 3), dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        ops.confusion(torch.from_numpy(y).cuda(), torch.from_numpy(p).cuda(), torch.from_numpy(proj).cuda(), n_proj, counts)
+    ref = np.zeros((n_proj + 1, 3), dtype=np.int64)
+    for j in range(n):                                        # experiment.py:476-483
+        k = int(2 * y[j] + p[j]) - 1
+        if k == -1:
+            continue
+        ref[proj[j], k] += 1
+        ref[n_proj, k] += 1
+    assert np.array_equal(counts.cpu().numpy(), 2 * ref)
