@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""Drop-in for the reference's ``experiment.py`` CLI, restricted to its one compute-heavy
+stage (reference experiment.py:693-714 dispatches setup|container|run|tests|scores|shap|figures).
+
+    python experiment.py scores        # reads ./tests.json, writes ./scores.pkl
+
+``scores`` keeps the reference's file names (experiment.py:34-35) and pickle schema
+(experiment.py:488-490,498-501) but runs on B200 GPUs through libf16_b200.so.  Under
+``torchrun`` (WORLD_SIZE > 1) the (dataset, fold) units are sharded over one process per GPU
+and the integer counts are all-reduced over NCCL; rank 0 writes the pickle.
+
+The other reference commands (data collection in Docker, collation, SHAP, LaTeX figures) are
+outside this repo's scope and raise the same ``ValueError`` the
+reference raises for an unrecognised command (experiment.py:712-714).
+
+Extra, non-reference commands used by the tests / bench:
+    python experiment.py synth N [SEED]     # writes a synthetic tests.json
+"""
+
+import os
+import sys
+
+TESTS_FILE = "tests.json"       # experiment.py:34
+SCORES_FILE = "scores.pkl"      # experiment.py:35
+
+
+def write_scores():
+    from flake16_framework_b200 import scores as S
+
+    def progress(done, total):
+        sys.stdout.write(f"{done}/{total - done}\r")
+        sys.stdout.flush()
+
+    n_streams = int(os.environ.get("F16_STREAMS", "8"))
+    _, wall = S.write_scores(TESTS_FILE, SCORES_FILE, n_streams=n_streams, progress=progress)
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stdout.write(f"\n216 configs in {wall:.1f}s\n")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        command, *args = sys.argv[1:]
+
+        if command == "scores" and not args:
+            write_scores()
+        elif command == "synth" and args:
+            from flake16_framework_b200 import synth
+            synth.make_tests_json(TESTS_FILE, int(args[0]), int(args[1]) if len(args) > 1 else 16)
+        else:
+            raise ValueError("Unrecognized command given.")
+    else:
+        raise ValueError("No command given.")

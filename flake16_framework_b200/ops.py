@@ -179,7 +179,7 @@ def knn(A, Q, k):
     return out
 
 
-def smote(X, y, n_min, n_maj, minority=1, seed=0, k_neighbors=5):
+def smote(X, y, n_min, n_maj, minority=1, seed=0, k_neighbors=5, idx_min=None):
     """SMOTE(random_state=seed).fit_resample on device.  X float64 [n,d], y uint8 [n].
     ``n_min`` / ``n_maj`` are the class counts (known on the host from the fold map, so no
     device->host read is needed).  The MT19937 draws (randint then uniform, imblearn
@@ -189,7 +189,8 @@ def smote(X, y, n_min, n_maj, minority=1, seed=0, k_neighbors=5):
     n_new = int(n_maj - n_min)
     if n_new == 0:
         return X, y
-    idx_min = torch.nonzero(y == minority).squeeze(1)          # original order
+    if idx_min is None:
+        idx_min = torch.nonzero(y == minority).squeeze(1)      # original order
     C = gather_rows_f64(X, idx_min)
     nn = knn(C, C, k_neighbors + 1)
     rs = np.random.RandomState(seed)

@@ -1,0 +1,313 @@
+"""The ``scores`` stage on B200: ``get_scores`` / ``write_scores`` of the reference
+(experiment.py:446-501) re-organised for the GPU.
+
+Reference shape: 216 independent ``get_scores(config)`` calls in a ``multiprocessing.Pool``
+(experiment.py:493-498), each re-parsing tests.json, re-running the preprocessing and re-doing
+the 10-fold loop with its own balancing + fit + predict + Python per-row confusion loop.
+
+Here the grid is de-duplicated: 2 label vectors x 2 feature sets x 3
+preprocessings = 12 datasets; the fold map depends only on the labels; a resampled training
+set is shared by the 3 models; the k=4 neighbour table of a training set serves both
+TomekLinks (column 1) and ENN (columns 1..3).  The unit of work is one (dataset, fold): it
+stages the fold on the device once and runs every requested (balancing, model) pair on it.
+Units are independent: they are spread over worker threads (one CUDA stream each, so several
+forests are in flight per GPU) and, with ``torch.distributed``, over ranks (one process per
+GPU); the only exchange step is one all-reduce of the integer confusion counts at the end.
+
+Results are FP/FN/TP per project and in total (int64, accumulated on the device by
+``f16_confusion``); precision / recall / F1 are derived on the host with the reference's own
+Python-float expressions, so they are bit-identical given identical counts.
+"""
+
+import itertools
+import pickle
+import queue
+import threading
+import time
+
+import numpy as np
+import torch
+
+from . import hostprep as hp
+from . import ops
+
+BALANCINGS = ("None", "Tomek Links", "SMOTE", "ENN", "SMOTE ENN", "SMOTE Tomek")     # experiment.py:87-94
+MODELS = ("Extra Trees", "Random Forest", "Decision Tree")                           # experiment.py:95-99
+MODEL_KIND = {"Extra Trees": ops.KIND_ET, "Random Forest": ops.KIND_RF, "Decision Tree": ops.KIND_DT}
+GRID_KEYS = (tuple(hp.FLAKY_TYPES), tuple(hp.FEATURE_SETS), tuple(hp.PREPROCESSINGS), BALANCINGS, MODELS)
+
+
+def all_config_keys():
+    return list(itertools.product(*GRID_KEYS))                                       # experiment.py:494
+
+
+class GridData:
+    """Host-side, config-independent preparation: parse once, 12 datasets, 2 fold maps."""
+
+    def __init__(self, parsed, configs, n_splits=10):
+        self.parsed = parsed
+        self.n_splits = n_splits
+        all_features, raw_labels, projects = parsed
+        self.projects = projects
+        # project ids in order of first appearance == insertion order of the reference's
+        # `scores = {proj: [0] * 6 for proj in projects}` (experiment.py:456)
+        uniq, first, inv = np.unique(projects, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(len(order))
+        self.proj_names = [projects[first[o]] for o in order]
+        self.proj_id = rank[inv].astype(np.int32)
+        self.n_proj = len(uniq)
+        self.datasets = {}      # (ft, fs, pre) -> float64 C-contiguous [N, d]
+        self.labels = {}        # ft -> bool[N]
+        self.folds = {}         # ft -> test_folds int[N]
+        for (ft, fs, pre) in sorted({c[:3] for c in configs}):
+            X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[ft], hp.FEATURE_SETS[fs])
+            self.datasets[(ft, fs, pre)] = np.ascontiguousarray(hp.preprocess(X, pre))
+            if ft not in self.labels:
+                self.labels[ft] = y
+                self.folds[ft] = hp.stratified_kfold_test_folds(y, n_splits, True, 0)
+
+
+class _DeviceData:
+    """Per-process device copies (uploaded once; 12 x <= 12.8 MB at 100 k rows)."""
+
+    def __init__(self, gd, device):
+        self.X = {k: torch.from_numpy(v).to(device) for k, v in gd.datasets.items()}
+        self.y = {k: torch.from_numpy(v.astype(np.uint8)).to(device) for k, v in gd.labels.items()}
+        self.proj = torch.from_numpy(gd.proj_id).to(device)
+        self.fold_idx = {}
+        for ft, tf in gd.folds.items():
+            for i, (tr, te) in enumerate(hp.kfold_split(tf, gd.n_splits)):
+                ytr = gd.labels[ft][tr]
+                c1 = int(ytr.sum())
+                self.fold_idx[(ft, i)] = (torch.from_numpy(tr).to(device), torch.from_numpy(te).to(device),
+                                          (len(tr) - c1, c1),
+                                          torch.from_numpy(np.flatnonzero(ytr)).to(device),
+                                          torch.from_numpy(np.flatnonzero(~ytr)).to(device))
+
+    def h2d_bytes(self):
+        b = sum(t.numel() * t.element_size() for t in self.X.values())
+        b += sum(t.numel() for t in self.y.values()) + self.proj.numel() * 4
+        b += sum((a.numel() + b_.numel()) * 8 for a, b_, *_ in self.fold_idx.values())
+        return b
+
+
+def _unit_cost(gd, unit, wanted):
+    (ft, fs, pre), fold = unit
+    d = gd.datasets[(ft, fs, pre)].shape[1]
+    n = gd.datasets[(ft, fs, pre)].shape[0]
+    cost = 0.0
+    for bal, models in wanted.items():
+        m = 2.0 if "SMOTE" in bal else 1.0
+        knn = (m * n) ** 2 * d * 1e-9 if bal != "None" and bal != "SMOTE" else 0.0
+        cost += knn + m * n * d * len(models) * 1e-3
+    return cost
+
+
+def _minority_clean_mask(counts, strategy):
+    if strategy == "all":
+        return 0b11
+    minority = 0 if counts[0] <= counts[1] else 1
+    return 0b11 & ~(1 << minority)
+
+
+def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers):
+    """One (dataset, fold): stage, resample per balancing, fit/predict/count per model."""
+    ds_key, fold = unit
+    ft = ds_key[0]
+    X64 = dd.X[ds_key]
+    d = X64.shape[1]
+    y_all = dd.y[ft]
+    tr_idx, te_idx, counts, pos_in_tr, neg_in_tr = dd.fold_idx[(ft, fold)]
+    Xte = ops.rows_f32(X64, te_idx)
+    yte = ops.gather_u8(y_all, te_idx)
+    pte = dd.proj[te_idx]
+    ytr = ops.gather_u8(y_all, tr_idx)
+    need64 = any(b != "None" for b in wanted)
+    Xtr64 = ops.gather_rows_f64(X64, tr_idx) if need64 else None
+    n_tr = tr_idx.shape[0]
+    minority = 0 if counts[0] <= counts[1] else 1
+
+    cache = {}
+
+    def nn4(tag, X):
+        if tag not in cache:
+            cache[tag] = ops.knn(X, X, 4)
+        return cache[tag]
+
+    def smoted():
+        if "smote" not in cache:
+            idx_min = pos_in_tr if minority == 1 else neg_in_tr
+            cache["smote"] = ops.smote(Xtr64, ytr, min(counts), max(counts), minority, 0, 5, idx_min=idx_min)
+        return cache["smote"]
+
+    def clean(kind, X, y, tag, strategy, cnts):
+        L = ops._ready()
+        nn = nn4(tag, X)
+        keep = torch.empty((X.shape[0],), dtype=torch.uint8, device=X.device)
+        mask = _minority_clean_mask(cnts, strategy)
+        fn = L.f16_tomek_keep if kind == "tomek" else L.f16_enn_keep
+        ops.check(fn(ops._ptr(nn), 4, ops._ptr(y), X.shape[0], mask, ops._ptr(keep), ops._stream()))
+        Xo, yo, _ = ops._compact(X, y, keep, 0 if kind == "tomek" else 1)
+        return Xo, yo
+
+    for bal in BALANCINGS:
+        if bal not in wanted:
+            continue
+        if bal == "None":
+            Xrow, yb = ops.rows_f32(X64, tr_idx), ytr
+        else:
+            if bal == "Tomek Links":
+                Xb, yb = clean("tomek", Xtr64, ytr, "tr", "auto", counts)
+            elif bal == "ENN":
+                Xb, yb = clean("enn", Xtr64, ytr, "tr", "auto", counts)
+            elif bal == "SMOTE":
+                Xb, yb = smoted()
+            elif bal == "SMOTE ENN":
+                Xs, ys = smoted()
+                Xb, yb = clean("enn", Xs, ys, "sm", "all", None)
+            elif bal == "SMOTE Tomek":
+                Xs, ys = smoted()
+                Xb, yb = clean("tomek", Xs, ys, "sm", "all", None)
+            Xrow = ops.rows_f32(Xb.contiguous())
+            yb = yb.contiguous()
+        models = wanted[bal]
+        sorted_idx = None
+        if any(m != "Extra Trees" for m in models):
+            sorted_idx = ops.argsort_columns(Xrow, d)
+        for model in MODELS:
+            if model not in models:
+                continue
+            ci = cfg_index[ds_key + (bal, model)]
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx)
+            e1.record()
+            pred = forest.predict(Xte)
+            e2.record()
+            ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
+            timers.append((ci, e0, e1, e2, forest))
+    return n_tr
+
+
+def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, device=None,
+             rank=0, world=1, progress=None, return_counts=False):
+    """Computes the scores dict for ``configs`` (default: the full 216 grid).
+
+    Returns {config_keys: [t_train / n_splits, t_test / n_splits, scores, scores_total]} - the
+    value layout of the reference's scores.pkl (experiment.py:488-490, :498)."""
+    configs = list(configs) if configs is not None else all_config_keys()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    ops._ready(device.index if device.index is not None else torch.cuda.current_device())
+    gd = GridData(parsed, configs, n_splits)
+    dd = _DeviceData(gd, device)
+    cfg_index = {c: i for i, c in enumerate(configs)}
+    counts_all = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
+    times = np.zeros((len(configs), 2), dtype=np.float64)
+
+    # (dataset, fold) units and what each must produce: {balancing: [models]}
+    wanted_by_ds = {}
+    for c in configs:
+        wanted_by_ds.setdefault(c[:3], {}).setdefault(c[3], []).append(c[4])
+    units = [(ds, f) for ds in wanted_by_ds for f in range(n_splits)]
+    units.sort(key=lambda u: -_unit_cost(gd, u, wanted_by_ds[u[0]]))
+    # longest-processing-time-first sharding over ranks
+    load = [0.0] * world
+    mine = []
+    for u in units:
+        r = int(np.argmin(load))
+        load[r] += _unit_cost(gd, u, wanted_by_ds[u[0]])
+        if r == rank:
+            mine.append(u)
+
+    q = queue.Queue()
+    for u in mine:
+        q.put(u)
+    errors = []
+    lock = threading.Lock()
+    done = [0]
+
+    def worker():
+        torch.cuda.set_device(device)
+        stream = torch.cuda.Stream(device=device)
+        timers = []
+        try:
+            with torch.cuda.stream(stream):
+                while True:
+                    try:
+                        u = q.get_nowait()
+                    except queue.Empty:
+                        break
+                    _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers)
+                    stream.synchronize()
+                    for ci, e0, e1, e2, forest in timers:
+                        forest.status()
+                        with lock:
+                            times[ci, 0] += e0.elapsed_time(e1) * 1e-3
+                            times[ci, 1] += e1.elapsed_time(e2) * 1e-3
+                        forest.free()
+                    timers.clear()
+                    with lock:
+                        done[0] += 1
+                        if progress:
+                            progress(done[0], len(mine))
+        except Exception as ex:  # propagate to the caller
+            with lock:
+                errors.append(ex)
+
+    n_thr = max(1, min(n_streams, len(mine)))
+    threads = [threading.Thread(target=worker, daemon=True) for _ in range(n_thr)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    torch.cuda.synchronize(device)
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(counts_all, op=dist.ReduceOp.SUM)          # the one exchange step
+        tt = torch.from_numpy(times).to(device)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        times = tt.cpu().numpy()
+    counts = counts_all.cpu().numpy()
+    if return_counts:
+        return configs, counts, times, gd
+    return assemble_scores(configs, counts, times, gd, n_splits)
+
+
+def assemble_scores(configs, counts, times, gd, n_splits=10):
+    """experiment.py:485-490: P/R/F from the integer counts with the reference's expressions."""
+    out = {}
+    for ci, config_keys in enumerate(configs):
+        scores = {}
+        for pid, name in enumerate(gd.proj_names):
+            fp, fn, tp = (int(v) for v in counts[ci, pid])
+            scores[name] = [fp, fn, tp, *hp.get_prf(fp, fn, tp)]
+        fp, fn, tp = (int(v) for v in counts[ci, gd.n_proj])
+        total = [fp, fn, tp, *hp.get_prf(fp, fn, tp)]
+        # the reference divides by the literal 10 (experiment.py:489)
+        out[tuple(config_keys)] = [times[ci, 0] / 10, times[ci, 1] / 10, scores, total]
+    return out
+
+
+def write_scores(tests_file="tests.json", scores_file="scores.pkl", **kw):
+    """``python experiment.py scores`` (experiment.py:493-501)."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl")
+    t0 = time.time()
+    parsed = hp.parse_tests(tests_file)
+    scores = run_grid(parsed, rank=rank, world=world, **kw)
+    if rank == 0:
+        with open(scores_file, "wb") as fd:
+            pickle.dump(scores, fd)
+    return scores, time.time() - t0
