@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py - the `scores` hot path benchmark (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the full 216-config grid (2 flaky types x 2 feature sets x 3
+preprocessings x 6 balancings x 3 models, 10-fold CV, 100-tree forests) over a synthetic
+100 000-test x 16-feature tests.json.  metric = configs/sec (BASELINE.json).
+  value : inputs already resident in HBM (12 preprocessed datasets + fold index maps).
+  e2e   : `flake16_framework_b200.scores.write_scores("tests.json" -> "scores.pkl")`, i.e. the
+          reference CLI path: JSON parse, host preprocessing, H2D of every dataset, the grid,
+          D2H of the counts, pickle.
+With N > 1 ranks the (dataset, fold) units are sharded over ranks (strong scaling: the grid is
+fixed) and the counts are all-reduced once.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "configs/sec for full `scores` grid"
+UNIT = "configs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-tests", type=int, default=100000)
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("F16_STREAMS", "8")))
+    ap.add_argument("--configs", default="grid216", help="grid216 | slice (1 dataset, 18 configs; for quick checks)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": "full scores grid: 216 configs x 10-fold CV, 100-tree forests, synthetic tests.json "
+                        "%d tests x 16 features (seed 16)" % args.n_tests if args.configs == "grid216" else
+                        "grid slice NOD/Flake16/Scaling: 18 configs x 10-fold, %d tests" % args.n_tests,
+            "n_tests": args.n_tests, "n_configs": 216 if args.configs == "grid216" else 18, "n_splits": 10,
+            "n_estimators": 100, "parallelism": "grid-sharded x%d" % args.gpus,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_sample(tests_file, steps_total):
+    """A bounded sample of the workload on the host cores through the oracle (the reference's
+    get_scores restated on the in-image scikit-learn), one single-threaded call chain per worker
+    like the reference's Pool(N_PROC).  Returns (config_equivalents, description, n_workers)."""
+    cores = os.cpu_count() or 1
+    base = [("NOD", "Flake16", "None", "None", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
+    smote = [("NOD", "Flake16", "None", "SMOTE", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
+    if steps_total <= 2:
+        tasks = base + smote
+    elif steps_total <= 6:
+        tasks = base
+    else:
+        tasks = base[:2]
+    desc = ("fold 1 of 10 of %d configs (%s) on the same tests.json, one process per task"
+            % (len(tasks), "; ".join("/".join(t[2:]) for t in tasks)))
+    return tasks, desc, min(cores, len(tasks))
+
+
+def run_cpu_sample(tests_file, tasks, workers):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_scores as R
+    t0 = time.perf_counter()
+    R.run_configs(tasks, tests_file, processes=workers, max_folds=1)
+    dt = time.perf_counter() - t0
+    return (len(tasks) / 10.0) / dt, dt          # config-equivalents per second
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from flake16_framework_b200 import synth
+    tmp = tempfile.mkdtemp(prefix="f16bench_ref")
+    tests_file = os.path.join(tmp, "tests.json")
+    synth.make_tests_json(tests_file, args.n_tests, 16)
+    tasks, desc, workers = cpu_sample(tests_file, args.steps + args.warmup)
+    for _ in range(args.warmup):
+        run_cpu_sample(tests_file, tasks, workers)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_cpu_sample(tests_file, tasks, workers)
+    dt = time.perf_counter() - t0
+    value = (len(tasks) / 10.0) * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc,
+                             "host_cores": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def roofline_probe(parsed, L):
+    """Dominant tree kernel (k_build_best, RandomForest 100 trees on one 90 000 x 16 fold):
+    algorithmic bytes per launch = 12 B x sum_{internal nodes} n_node_samples x (F_eval + 1)
+    (SURVEY.md 8(d)), F_eval = max_features = 4; duration = CUDA events around that kernel on
+    its launch stream (inside f16_forest_fit)."""
+    import numpy as np
+    import torch
+    from flake16_framework_b200 import hostprep as hp, ops
+    X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY, hp.FEATURE_SETS["Flake16"])
+    X = np.ascontiguousarray(X)
+    tr, _ = next(iter(hp.kfold_split(hp.stratified_kfold_test_folds(y))))
+    Xd = torch.from_numpy(X).cuda()
+    Xrow = ops.rows_f32(Xd, torch.from_numpy(tr).cuda())
+    ytr = torch.from_numpy(y[tr].astype(np.uint8)).cuda()
+    sidx = ops.argsort_columns(Xrow, 16)
+    L.f16_set_profiling(1)
+    ms, alg = [], None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for it in range(4):
+        flush.fill_(it)
+        f = ops.forest_fit(Xrow, ytr, 16, ops.KIND_RF, 100, 0, sidx)
+        t = L.f16_forest_build_ms(f._h)
+        if it > 0:
+            ms.append(t)
+        if alg is None:
+            tot = 0
+            counts = f.node_counts()
+            for ti in range(100):
+                tr_ = f.export_tree(ti, int(counts[ti]))
+                tot += int(tr_["n_node_samples"][tr_["children_left"] >= 0].sum())
+            alg = 12.0 * tot * (4 + 1)
+        f.free()
+    L.f16_set_profiling(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    avg_ms = sum(ms) / len(ms)
+    achieved = alg / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_build_best_bytes_per_launch")
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": "k_build_best<16> (RandomForest, 100 trees, 90000x16 fold)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": alg, "kernel_ms": avg_ms, "traffic": traffic}
+
+
+def ours_arm(args):
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from flake16_framework_b200 import _lib, hostprep as hp, scores as S, synth
+    L = _lib.lib()
+    _lib.init(local)
+
+    tmp = tempfile.mkdtemp(prefix="f16bench_r%d_" % rank)
+    tests_file = os.path.join(tmp, "tests.json")
+    synth.make_tests_json(tests_file, args.n_tests, 16)          # every rank: same seeded table
+    parsed = hp.parse_tests(tests_file)
+    configs = S.all_config_keys()
+    if args.configs == "slice":
+        configs = [c for c in configs if c[:3] == ("NOD", "Flake16", "Scaling")]
+    prepared = S.prepare(parsed, configs, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def one_step():
+        return S.run_grid(parsed, configs, n_streams=args.streams, device=dev, rank=rank, world=world,
+                          prepared=prepared, return_counts=True)
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    L.f16_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    for it in range(args.steps):
+        flush.fill_(it & 0xff)
+        barrier()
+        ev0.record()
+        one_step()
+        torch.cuda.synchronize(dev)
+        ev1.record()
+        barrier()
+        total_ms += ev0.elapsed_time(ev1)
+    launches = int(L.f16_launch_count(0))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    n_cfg = len(configs)
+    value = n_cfg * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: tests.json on disk -> scores.pkl through the public write_scores()
+    e2e = None
+    if not args.no_e2e:
+        scores_file = os.path.join(tmp, "scores.pkl")
+        kw = dict(n_streams=args.streams, configs=configs)
+        S.write_scores(tests_file, scores_file, **kw)                # warm
+        e2e_steps = args.steps if total_ms / args.steps < 30e3 else 1
+        barrier()
+        t0 = time.perf_counter()
+        stats = None
+        for _ in range(e2e_steps):
+            _, _, stats = S.write_scores(tests_file, scores_file, return_stats=True, **kw)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_cfg * e2e_steps / float(dt.item()), "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": stats["h2d_bytes"], "d2h_bytes_per_step": stats["d2h_bytes"],
+               "includes": "json parse, host preprocessing, H2D, grid, D2H, pickle"}
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 criterion / f32 features / int counts",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(ln.item()),
+            "trees_per_s": (n_cfg // 3) * 10 * 201 * args.steps / (total_ms * 1e-3) if args.configs == "grid216" else None}
+    if world == 1:
+        line["roofline"] = roofline_probe(parsed, L)
+        if not args.no_cpu_baseline:
+            tasks, desc, workers = cpu_sample(tests_file, 1)
+            v, dt = run_cpu_sample(tests_file, tasks, workers)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+                                    "sample": desc + " (%.1f s)" % dt, "host_cores": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours_arm(a)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()

@@ -64,6 +64,9 @@ SIGNATURES = {
     "f16_last_error": ([], ctypes.c_char_p),
     "f16_version": ([], c_int),
     "f16_init": ([c_int], c_int),
+    "f16_launch_count": ([c_int], ctypes.c_longlong),
+    "f16_set_profiling": ([c_int], None),
+    "f16_forest_build_ms": ([c_void_p], ctypes.c_double),
     "f16_gather_rows_f32": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_gather_rows_f64": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_gather_u8": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),

@@ -13,6 +13,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+extern "C" void f16_count_launch(int n);
+extern "C" long long f16_launch_count(int reset);
+
 #define F16_OK 0
 #define F16_ERR_INVALID -1
 #define F16_ERR_CUDA -2

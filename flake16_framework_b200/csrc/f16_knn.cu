@@ -79,14 +79,14 @@ template <int D>
 static int launch_k(const double* A, int n, const double* Q, int nq, int k, int32_t* out, cudaStream_t st) {
     int grid = (nq + KT - 1) / KT;
     switch (k) {
-        case 1: k_knn<D, 1><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 2: k_knn<D, 2><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 3: k_knn<D, 3><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 4: k_knn<D, 4><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 5: k_knn<D, 5><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 6: k_knn<D, 6><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 7: k_knn<D, 7><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
-        case 8: k_knn<D, 8><<<grid, KT, 0, st>>>(A, n, Q, nq, out); break;
+        case 1: k_knn<D, 1><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 2: k_knn<D, 2><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 3: k_knn<D, 3><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 4: k_knn<D, 4><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 5: k_knn<D, 5><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 6: k_knn<D, 6><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 7: k_knn<D, 7><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
+        case 8: k_knn<D, 8><<<grid, KT, 0, st>>>(A, n, Q, nq, out); f16_count_launch(1); break;
         default: return F16_ERR_INVALID;
     }
     return F16_OK;

@@ -22,6 +22,16 @@ extern "C" void f16_set_error(const char* fmt, ...) {
 extern "C" const char* f16_last_error(void) { return g_err; }
 extern "C" int f16_version(void) { return 100; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" void f16_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long f16_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+static std::atomic<int> g_profiling{0};
+extern "C" void f16_set_profiling(int on) { g_profiling.store(on); }
+extern "C" int f16_get_profiling(void) { return g_profiling.load(); }
+
 #define CUDA_TRY(x)                                                                     \
     do {                                                                                \
         cudaError_t e_ = (x);                                                           \
@@ -73,6 +83,7 @@ extern "C" int f16_gather_rows_f32(const double* X_dev, int32_t d, const int64_t
     int dp = (d <= 8) ? 8 : 16;
     int64_t tot = n_out * dp;
     k_gather_cast<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X_dev, d, idx_dev, n_out, dp, out_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -82,6 +93,7 @@ extern "C" int f16_gather_rows_f64(const double* X_dev, int32_t d, const int64_t
     if (n_out == 0) return F16_OK;
     int64_t tot = n_out * d;
     k_gather_f64<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X_dev, d, idx_dev, n_out, out_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -89,6 +101,7 @@ extern "C" int f16_gather_u8(const uint8_t* y_dev, const int64_t* idx_dev, int64
     if (!y_dev || !out_dev || !idx_dev || n_out < 0) { f16_set_error("f16_gather_u8: bad arguments"); return F16_ERR_INVALID; }
     if (n_out == 0) return F16_OK;
     k_gather_u8<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y_dev, idx_dev, n_out, out_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -121,6 +134,7 @@ extern "C" int f16_smote_generate(const double* C_dev, int64_t n_min, int32_t d,
     if (n_new == 0) return F16_OK;
     int64_t tot = n_new * d;
     k_smote<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(C_dev, d, nn_dev, k, sample_idx_dev, steps_dev, n_new, Xnew_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -155,6 +169,7 @@ extern "C" int f16_tomek_keep(const int32_t* nn_dev, int32_t kk, const uint8_t* 
     if (!nn_dev || !y_dev || !keep_dev || kk < 2 || n < 0) { f16_set_error("f16_tomek_keep: bad arguments"); return F16_ERR_INVALID; }
     if (n == 0) return F16_OK;
     k_tomek_keep<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nn_dev, kk, y_dev, n, clean_mask, keep_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -163,6 +178,7 @@ extern "C" int f16_enn_keep(const int32_t* nn_dev, int32_t kk, const uint8_t* y_
     if (!nn_dev || !y_dev || !keep_dev || kk < 2 || n < 0) { f16_set_error("f16_enn_keep: bad arguments"); return F16_ERR_INVALID; }
     if (n == 0) return F16_OK;
     k_enn_keep<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nn_dev, kk, y_dev, n, clean_mask, keep_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }
@@ -250,8 +266,11 @@ extern "C" int f16_compact_rows(const double* X_dev, const uint8_t* y_dev, const
     unsigned long long* bs = nullptr;
     CUDA_TRY(cudaMallocAsync((void**)&bs, sizeof(unsigned long long) * (nb + 1), st));
     k_compact_count<<<nb, CB, 0, st>>>(keep_dev, y_dev, n, bs);
+    f16_count_launch(1);
     k_compact_scan<<<1, 1024, 0, st>>>(bs, nb, n_out_dev);
+    f16_count_launch(1);
     k_compact_scatter<<<nb, CB, 0, st>>>(X_dev, y_dev, keep_dev, n, d, grouped, bs, nb, Xout_dev, yout_dev, src_index_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(bs, st));
     return F16_OK;
@@ -287,6 +306,7 @@ extern "C" int f16_confusion(const uint8_t* y_dev, const uint8_t* pred_dev, cons
     if (grid > 296) grid = 296;
     k_confusion<<<grid, 256, sizeof(unsigned int) * (n_proj + 1) * 3, (cudaStream_t)stream>>>(
         y_dev, pred_dev, proj_dev, n, n_proj, (unsigned long long*)counts_dev);
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     return F16_OK;
 }

@@ -140,8 +140,11 @@ extern "C" int f16_argsort_columns(const float* X_dev, int64_t n, int32_t d, int
         uint32_t* vout = (pass & 1) ? vb : va;
         int first = pass == 0;
         k_radix_hist<<<grid, ST, 0, st>>>(X_dev, dp, kin, (int)n, pass * 8, first, hist, nblocks);
+        f16_count_launch(1);
         k_radix_scan<<<d, 1024, 0, st>>>(hist, nblocks);
+        f16_count_launch(1);
         k_radix_scatter<<<grid, ST, 0, st>>>(X_dev, dp, kin, vin, kout, vout, (int)n, pass * 8, first, hist, nblocks);
+        f16_count_launch(1);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(ka, st));

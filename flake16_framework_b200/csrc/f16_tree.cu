@@ -680,6 +680,7 @@ __global__ void k_predict_reduce(const int2* __restrict__ leaf, int n, int n_tre
 #include <vector>
 
 extern "C" void f16_set_error(const char* fmt, ...);
+extern "C" int f16_get_profiling(void);
 
 #define CUDA_TRY(x)                                                                     \
     do {                                                                                \
@@ -725,6 +726,7 @@ extern "C" int f16_bootstrap_counts(const uint32_t* tree_seed_host, int32_t n_tr
     CUDA_TRY(cudaMemcpyAsync(seeds_dev, tree_seed_host, sizeof(uint32_t) * n_trees, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(w_dev, 0, stride * n_trees, st));
     k_bootstrap<<<n_trees, NT, 0, st>>>(seeds_dev, (int)n, (uint32_t*)w_dev, (int)(stride / 4));
+    f16_count_launch(1);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(seeds_dev, st));
     return F16_OK;
@@ -790,6 +792,13 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
             dyn = sizeof(uint32_t) * (size_t)P.side_words;
         }
     }
+    if (f16_get_profiling()) {
+        CUDA_TRY(cudaEventCreate(&F->ev0));
+        CUDA_TRY(cudaEventCreate(&F->ev1));
+        F->has_ev = 1;
+        CUDA_TRY(cudaEventRecord(F->ev0, st));
+    }
+    f16_count_launch(1);
     if (best) {
         if (dp == 8) {
             CUDA_TRY(cudaFuncSetAttribute(k_build_best<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * F16_SIDE_SMEM_MAX_WORDS));
@@ -803,6 +812,7 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
         else k_build_random<16><<<n_trees, NT, 0, st>>>(P);
     }
     CUDA_TRY(cudaGetLastError());
+    if (F->has_ev) CUDA_TRY(cudaEventRecord(F->ev1, st));
     CUDA_TRY(cudaFreeAsync(P.buf, st));
     CUDA_TRY(cudaFreeAsync(P.stack, st));
     CUDA_TRY(cudaFreeAsync(rr_dev, st));
@@ -822,6 +832,7 @@ extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64
     if (F->dp == 8) k_predict_walk<8><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);
     else k_predict_walk<16><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);
     CUDA_TRY(cudaGetLastError());
+    f16_count_launch(2);
     k_predict_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(leaf, (int)n, F->n_trees, pred_dev);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(leaf, st));
@@ -839,6 +850,16 @@ extern "C" int f16_forest_status(const f16_forest* F, void* stream) {
 }
 
 extern "C" int f16_forest_n_trees(const f16_forest* F) { return F ? F->n_trees : 0; }
+
+// Synchronises on the build kernel's end event; milliseconds spent in the tree-building
+// kernel alone (needs f16_set_profiling(1) before the fit), or -1.
+extern "C" double f16_forest_build_ms(const f16_forest* F) {
+    if (!F || !F->has_ev) return -1.0;
+    float ms = -1.f;
+    if (cudaEventSynchronize(F->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, F->ev0, F->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 extern "C" int f16_forest_node_counts(const f16_forest* F, int32_t* counts_host, void* stream) {
     if (!F || !counts_host) { f16_set_error("f16_forest_node_counts: bad arguments"); return F16_ERR_INVALID; }
@@ -880,5 +901,6 @@ extern "C" void f16_forest_free(f16_forest* F, void* stream) {
     if (F->nodes) cudaFreeAsync(F->nodes, st);
     if (F->node_count) cudaFreeAsync(F->node_count, st);
     if (F->err) cudaFreeAsync(F->err, st);
+    if (F->has_ev) { cudaEventDestroy(F->ev0); cudaEventDestroy(F->ev1); }
     free(F);
 }

@@ -49,7 +49,8 @@ struct f16_forest {
     F16Node* nodes;      // device [n_trees][node_cap]
     int32_t* node_count; // device [n_trees]
     int32_t* err;        // device
-    uint32_t tree_seed[1];  // (unused placeholder; seeds kept host-side in the .cu)
+    cudaEvent_t ev0, ev1;   // around the tree-building kernel when profiling is on
+    int has_ev;
 };
 
 #define F16_KIND_DT 0

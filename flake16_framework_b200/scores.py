@@ -105,6 +105,25 @@ def _unit_cost(gd, unit, wanted):
     return cost
 
 
+def plan_units(gd, configs, n_splits, world):
+    """(dataset, fold) units, what each must produce ({balancing: [models]}), and their
+    longest-processing-time-first assignment to ``world`` ranks (deterministic, so every rank
+    derives the same plan without communicating)."""
+    wanted_by_ds = {}
+    for c in configs:
+        wanted_by_ds.setdefault(tuple(c[:3]), {}).setdefault(c[3], []).append(c[4])
+    units = [(ds, f) for ds in wanted_by_ds for f in range(n_splits)]
+    cost = {u: _unit_cost(gd, u, wanted_by_ds[u[0]]) for u in units}
+    units.sort(key=lambda u: (-cost[u], u))
+    load = [0.0] * world
+    shards = [[] for _ in range(world)]
+    for u in units:
+        r = int(np.argmin(load))
+        load[r] += cost[u]
+        shards[r].append(u)
+    return wanted_by_ds, shards
+
+
 def _minority_clean_mask(counts, strategy):
     if strategy == "all":
         return 0b11
@@ -191,8 +210,21 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers)
     return n_tr
 
 
+def prepare(parsed, configs=None, device=None, n_splits=10):
+    """Host preparation + upload: returns (GridData, device copies).  bench.py uses this to
+    time the grid with its inputs already resident in HBM."""
+    configs = list(configs) if configs is not None else all_config_keys()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    ops._ready(device.index if device.index is not None else torch.cuda.current_device())
+    gd = GridData(parsed, configs, n_splits)
+    dd = _DeviceData(gd, device)
+    torch.cuda.synchronize(device)
+    return gd, dd
+
+
 def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, device=None,
-             rank=0, world=1, progress=None, return_counts=False):
+             rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None):
     """Computes the scores dict for ``configs`` (default: the full 216 grid).
 
     Returns {config_keys: [t_train / n_splits, t_test / n_splits, scores, scores_total]} - the
@@ -200,27 +232,15 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
     configs = list(configs) if configs is not None else all_config_keys()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    ops._ready(device.index if device.index is not None else torch.cuda.current_device())
-    gd = GridData(parsed, configs, n_splits)
-    dd = _DeviceData(gd, device)
+    gd, dd = prepared if prepared is not None else prepare(parsed, configs, device, n_splits)
+    if stats is not None:
+        stats["h2d_bytes"] = dd.h2d_bytes()
     cfg_index = {c: i for i, c in enumerate(configs)}
     counts_all = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
     times = np.zeros((len(configs), 2), dtype=np.float64)
 
-    # (dataset, fold) units and what each must produce: {balancing: [models]}
-    wanted_by_ds = {}
-    for c in configs:
-        wanted_by_ds.setdefault(c[:3], {}).setdefault(c[3], []).append(c[4])
-    units = [(ds, f) for ds in wanted_by_ds for f in range(n_splits)]
-    units.sort(key=lambda u: -_unit_cost(gd, u, wanted_by_ds[u[0]]))
-    # longest-processing-time-first sharding over ranks
-    load = [0.0] * world
-    mine = []
-    for u in units:
-        r = int(np.argmin(load))
-        load[r] += _unit_cost(gd, u, wanted_by_ds[u[0]])
-        if r == rank:
-            mine.append(u)
+    wanted_by_ds, shards = plan_units(gd, configs, n_splits, world)
+    mine = shards[rank]
 
     q = queue.Queue()
     for u in mine:
@@ -274,6 +294,8 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         times = tt.cpu().numpy()
     counts = counts_all.cpu().numpy()
+    if stats is not None:
+        stats["d2h_bytes"] = counts.nbytes + times.nbytes
     if return_counts:
         return configs, counts, times, gd
     return assemble_scores(configs, counts, times, gd, n_splits)
@@ -294,9 +316,11 @@ def assemble_scores(configs, counts, times, gd, n_splits=10):
     return out
 
 
-def write_scores(tests_file="tests.json", scores_file="scores.pkl", **kw):
+def write_scores(tests_file="tests.json", scores_file="scores.pkl", return_stats=False, **kw):
     """``python experiment.py scores`` (experiment.py:493-501)."""
     import os
+    stats = {}
+    kw["stats"] = stats
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
@@ -310,4 +334,6 @@ def write_scores(tests_file="tests.json", scores_file="scores.pkl", **kw):
     if rank == 0:
         with open(scores_file, "wb") as fd:
             pickle.dump(scores, fd)
+    if return_stats:
+        return scores, time.time() - t0, stats
     return scores, time.time() - t0

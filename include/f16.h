@@ -39,6 +39,12 @@ const char* f16_last_error(void);
 int f16_version(void);
 /* Selects the device and keeps the stream-ordered memory pool from trimming. */
 int f16_init(int device);
+/* Number of kernels this library has launched (reset != 0 returns the count and zeroes it). */
+long long f16_launch_count(int reset);
+/* When on, f16_forest_fit brackets its tree-building kernel with CUDA events on the caller's
+ * stream; f16_forest_build_ms() then waits for that kernel and returns its duration (ms). */
+void f16_set_profiling(int on);
+double f16_forest_build_ms(const f16_forest* forest);
 
 /* ---- data staging ------------------------------------------------------------------
  * features[train] / features[test] (experiment.py:459-460) fused with the float32 cast that

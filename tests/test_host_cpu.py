@@ -1,0 +1,177 @@
+"""CPU tests (no GPU): host logic, oracle vs golden fixtures, C-ABI surface."""
+import ctypes
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import make_dataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _parsed(n):
+    from flake16_framework_b200 import hostprep as hp, synth
+    return hp.tests_to_arrays(synth.make_tests_dict(n, 16))
+
+
+@pytest.mark.parametrize("fs", ["Flake16", "FlakeFlagger"])
+def test_hostprep_bit_exact_vs_sklearn(fs):
+    """A1-A3: load/scale/PCA/fold maps must be bit-identical to what the reference computes."""
+    from sklearn.decomposition import PCA
+    from sklearn.model_selection import StratifiedKFold
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from flake16_framework_b200 import hostprep as hp
+    parsed = _parsed(3000)
+    for ft in ("NOD", "OD"):
+        X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[ft], hp.FEATURE_SETS[fs])
+        assert np.array_equal(hp.StandardScaler().fit_transform(X), StandardScaler().fit_transform(X))
+        ref = Pipeline([("s", StandardScaler()), ("p", PCA(random_state=0))]).fit_transform(X)
+        assert np.array_equal(hp.ScalePCA().fit_transform(X), ref)
+        tf = hp.stratified_kfold_test_folds(y)
+        for (a, b), (c, d) in zip(hp.kfold_split(tf), StratifiedKFold(10, shuffle=True, random_state=0).split(X, y)):
+            assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_load_feat_lab_proj_matches_reference_expression(tmp_path):
+    import json
+    import ref_scores as R
+    from flake16_framework_b200 import hostprep as hp, synth
+    p = str(tmp_path / "tests.json")
+    synth.make_tests_json(p, 500, 3)
+    parsed = hp.parse_tests(p)
+    for ft, lab in hp.FLAKY_TYPES.items():
+        for fs, cols in hp.FEATURE_SETS.items():
+            a = hp.feat_lab_proj(parsed, lab, cols)
+            b = R.load_feat_lab_proj(lab, cols, p)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+            assert a[0].flags["F_CONTIGUOUS"] == b[0].flags["F_CONTIGUOUS"]
+
+
+def test_get_prf():
+    from flake16_framework_b200 import hostprep as hp
+    assert hp.get_prf(0, 0, 0) == (None, None, None)
+    assert hp.get_prf(1, 0, 0) == (0.0, None, None)
+    assert hp.get_prf(0, 1, 0) == (None, 0.0, None)
+    assert hp.get_prf(1, 1, 0) == (0.0, 0.0, None)
+    assert hp.get_prf(1, 3, 1) == (0.5, 0.25, 2 * 0.5 * 0.25 / (0.5 + 0.25))
+
+
+def test_tree_seeds_match_numpy():
+    """A4: per-tree seeds as sklearn derives them (host code inside the shared library)."""
+    from flake16_framework_b200 import ops
+    for seed in (0, 1, 12345):
+        ts, rr = ops.tree_seeds(seed, ops.KIND_RF, 100)
+        rs = np.random.RandomState(seed)
+        assert list(ts) == [rs.randint(np.iinfo(np.int32).max) for _ in range(100)]
+        assert list(rr) == [np.random.RandomState(int(s)).randint(0, 2147483647) for s in ts]
+        ts, rr = ops.tree_seeds(seed, ops.KIND_DT, 1)
+        assert ts[0] == seed and rr[0] == np.random.RandomState(seed).randint(0, 2147483647)
+    assert list(ops.tree_seeds(0, ops.KIND_ET, 3)[0]) == [209652396, 398764591, 924231285]
+
+
+def test_abi_exports_every_declared_symbol():
+    from flake16_framework_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "f16.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(f16_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), "library does not export %s" % name
+        assert name in _lib.SIGNATURES, "no ctypes signature for %s" % name
+    out = subprocess.check_output(["nm", "-D", _lib.LIB_PATH]).decode()
+    assert "f16_forest_fit" in out
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from flake16_framework_b200 import estimators as E, _lib
+    X, y, _ = make_dataset(300)
+    with pytest.raises(Exception):
+        E.ExtraTreesClassifier(random_state=0).fit(X, y)
+
+
+def test_product_never_imports_oracle_or_sklearn():
+    for root, _, files in os.walk(os.path.join(ROOT, "flake16_framework_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import sklearn" not in src and "from sklearn" not in src, f
+                assert "ref_scores" not in src and "samplers_np" not in src, f
+    src = open(os.path.join(ROOT, "experiment.py")).read()
+    assert "sklearn" not in src and "oracle" not in src
+
+
+GOLD_CFGS = [("NOD", "Flake16", "None", "None", "Decision Tree"),
+             ("NOD", "Flake16", "None", "None", "Random Forest"),
+             ("OD", "FlakeFlagger", "Scaling", "SMOTE", "Extra Trees"),
+             ("NOD", "Flake16", "PCA", "SMOTE ENN", "Extra Trees"),
+             ("OD", "Flake16", "None", "Tomek Links", "Decision Tree"),
+             ("OD", "FlakeFlagger", "PCA", "ENN", "Random Forest"),
+             ("NOD", "FlakeFlagger", "None", "SMOTE Tomek", "Decision Tree")]
+
+
+def test_oracle_pinned_against_reference_golden(tmp_path):
+    """The oracle restatement (oracle/ref_scores.py) reproduces what the reference's own
+    get_scores produced here (tests/golden/make_golden.py), count for count."""
+    import ref_scores as R
+    from flake16_framework_b200 import synth
+    gold = pickle.load(open(os.path.join(GOLD, "scores_n1500_seed16.pkl"), "rb"))
+    p = str(tmp_path / "tests.json")
+    synth.make_tests_json(p, 1500, 16)
+    for cfg in GOLD_CFGS:
+        _, (keys, _, _, per_proj, total) = R.get_scores(cfg, p, R.make_config_grid())
+        g_proj, g_total = gold[cfg]
+        assert [int(v) for v in total[:3]] == g_total, cfg
+        assert {str(k): [int(x) for x in v[:3]] for k, v in per_proj.items()} == g_proj, cfg
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from flake16_framework_b200 import scores as S, hostprep as hp, synth
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(400, 16))
+    configs = S.all_config_keys()
+    gd = S.GridData(parsed, configs)
+    wanted, shards = S.plan_units(gd, configs, 10, world)
+    cfg_index = {c: i for i, c in enumerate(configs)}
+    counts = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64)
+    for (ds, fold) in shards[rank]:                      # fake, deterministic per-(unit, config) counts
+        for bal, models in wanted[ds].items():
+            for m in models:
+                ci = cfg_index[ds + (bal, m)]
+                counts[ci] += (fold + 1) * (ci + 1)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)        # the path's one exchange step
+    if rank == 0:
+        q.put((counts.numpy(), [len(s) for s in shards]))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_and_reduce():
+    """N>1 path on CPU (gloo): the unit plan is a partition and the reduced counts equal the
+    single-process totals."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    counts, sizes = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+    assert sum(sizes) == 120 and abs(sizes[0] - sizes[1]) <= 30
+    expect = np.array([sum(f + 1 for f in range(10)) * (ci + 1) for ci in range(216)])
+    assert np.array_equal(counts[:, 0, 0], expect)
