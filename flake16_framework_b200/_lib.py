@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libf16_b200.so")
 # (source, extra flags).  -fmad=false wherever float64 expressions must round like the CPU.
 _SOURCES = (
     ("f16_tree.cu", ["-fmad=false"]),
+    ("f16_tree_random.cu", ["-fmad=false"]),
+    ("f16_tree_best.cu", ["-fmad=false"]),
     ("f16_misc.cu", ["-fmad=false"]),
     ("f16_sort.cu", []),
     ("f16_knn.cu", []),

@@ -1,0 +1,157 @@
+// Device-side pieces shared by the two tree-building kernels (random / best splitter).
+#pragma once
+#include "f16_tree.cuh"
+#include <math.h>
+
+#define NT 256
+#define NW (NT / 32)
+#define F16_EPS 2.220446049250313e-16
+#define SSTK 64     // stack records cached in shared memory (deeper ones spill to global)
+
+// ------------------------------------------------------------------ shared control block
+struct Ctl {
+    int start, end, parent, c0, c1, n_const, is_left, depth;
+    uint32_t const_mask;
+    int in_smem;
+    int done, leaf, split;
+    int ncand;
+    int best_f;
+    double best_thr;
+    int n_left, l0, l1;
+    int n_const_out;
+    uint32_t const_mask_out;
+    int node_id;
+    unsigned long long win_key;
+    int sp, node_count;
+};
+
+// Fisher-Yates feature-draw state that persists across the nodes of a tree
+// (sklearn Splitter.features / constant_features / rand_r_state).
+struct DrawState {
+    int features[F16_MAX_D];
+    int const_feats[F16_MAX_D];
+    uint32_t rng;
+};
+
+struct TreeStack {
+    F16StackRec* smem;   // [SSTK]
+    F16StackRec* gmem;   // [stack_cap]
+    __device__ __forceinline__ F16StackRec get(int i) const { return i < SSTK ? smem[i] : gmem[i]; }
+    __device__ __forceinline__ void put(int i, const F16StackRec& r) const { if (i < SSTK) smem[i] = r; else gmem[i] = r; }
+};
+
+__device__ __forceinline__ double gini_of(double a, double b, double w) {
+    double sq = 0.0;
+    sq = sq + a * a;
+    sq = sq + b * b;
+    return 1.0 - sq / (w * w);
+}
+
+// proxy_impurity_improvement for Gini (sklearn/tree/_criterion.pyx:147-163, :647-687)
+__device__ __forceinline__ double gini_proxy(int l0, int l1, int t0, int t1) {
+    double L0 = (double)l0, L1 = (double)l1;
+    double R0 = (double)(t0 - l0), R1 = (double)(t1 - l1);
+    double wl = L0 + L1, wr = R0 + R1;
+    double gl = gini_of(L0, L1, wl);
+    double gr = gini_of(R0, R1, wr);
+    return (-wr * gr) - wl * gl;
+}
+
+// impurity_improvement (sklearn/tree/_criterion.pyx:165-199) + the builder's
+// `improvement + EPSILON < min_impurity_decrease` test (_tree.pyx:246-252), min_dec = 0.
+__device__ __forceinline__ bool improvement_ok(int l0, int l1, int t0, int t1, double W_total) {
+    double L0 = (double)l0, L1 = (double)l1;
+    double R0 = (double)(t0 - l0), R1 = (double)(t1 - l1);
+    double wl = L0 + L1, wr = R0 + R1, wn = (double)t0 + (double)t1;
+    double imp = gini_of((double)t0, (double)t1, wn);
+    double gl = gini_of(L0, L1, wl);
+    double gr = gini_of(R0, R1, wr);
+    double improvement = (wn / W_total) * (imp - (wr / wn * gr) - (wl / wn * gl));
+    return !(improvement + F16_EPS < 0.0);
+}
+
+// the builder's leaf pre-test (_tree.pyx:223-240): n_node_samples < 2 or impurity <= EPSILON
+__device__ __forceinline__ bool leaf_pretest(int n_node, int c0, int c1) {
+    double wn = (double)c0 + (double)c1;
+    return (n_node < 2) || (gini_of((double)c0, (double)c1, wn) <= F16_EPS);
+}
+
+// one thread: write node, link to parent, push children (right first: left is popped first)
+__device__ __forceinline__ void finish_node(Ctl& c, const F16FitParams& P, F16Node* nodes, const TreeStack& stk) {
+    int id = c.node_count++;
+    if (id >= P.node_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; return; }
+    F16Node nd;
+    nd.thr = c.split ? c.best_thr : -2.0;
+    nd.feature = c.split ? c.best_f : -2;
+    nd.right = -1;
+    nd.c0 = c.c0; nd.c1 = c.c1; nd.n = c.end - c.start; nd.depth = c.depth;
+    nodes[id] = nd;
+    if (c.parent >= 0 && !c.is_left) nodes[c.parent].right = id;
+    c.node_id = id;
+    if (c.split) {
+        if (c.sp + 2 > P.stack_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; return; }
+        F16StackRec r;
+        r.parent = id; r.depth = c.depth + 1; r.n_const = (int16_t)c.n_const_out;
+        r.const_mask = c.const_mask_out; r.pad = (uint8_t)c.in_smem;
+        r.start = c.start + c.n_left; r.end = c.end; r.c0 = c.c0 - c.l0; r.c1 = c.c1 - c.l1; r.is_left = 0;
+        stk.put(c.sp++, r);
+        r.start = c.start; r.end = c.start + c.n_left; r.c0 = c.l0; r.c1 = c.l1; r.is_left = 1;
+        stk.put(c.sp++, r);
+    }
+}
+
+// one thread: pop + leaf pre-test
+__device__ __forceinline__ void pop_node(Ctl& c, const TreeStack& stk) {
+    if (c.sp == 0) { c.done = 1; return; }
+    F16StackRec r = stk.get(--c.sp);
+    c.start = r.start; c.end = r.end; c.parent = r.parent; c.c0 = r.c0; c.c1 = r.c1;
+    c.n_const = r.n_const; c.const_mask = r.const_mask; c.is_left = r.is_left; c.depth = r.depth;
+    c.in_smem = r.pad;
+    c.leaf = leaf_pretest(r.end - r.start, r.c0, r.c1);
+    c.split = 0; c.ncand = 0;
+    c.n_const_out = r.n_const; c.const_mask_out = r.const_mask;
+}
+
+// ------------------------------------------------------------------ stable block partition (one array)
+// PU sub-tiles of NT elements per barrier: all loads of a round are issued before use.
+#define PU 4
+template <class Pred>
+__device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* dst, int start, int n, int n_left,
+                                                Pred pred, int (*s_wcnt)[PU][NW]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int run_l = 0, buf = 0;
+    for (int base = 0; base < n; base += NT * PU, buf ^= 1) {
+        uint32_t e[PU]; bool valid[PU], left[PU]; unsigned bal[PU];
+#pragma unroll
+        for (int j = 0; j < PU; j++) {
+            int p = base + j * NT + tid;
+            valid[j] = p < n;
+            e[j] = valid[j] ? src[start + p] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < PU; j++) left[j] = valid[j] && pred(e[j]);
+#pragma unroll
+        for (int j = 0; j < PU; j++) {
+            bal[j] = __ballot_sync(F16_FULL, left[j]);
+            if (lane == 0) s_wcnt[buf][j][warp] = __popc(bal[j]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PU; j++) {
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int q = 0; q < NW; q++) { int cq = s_wcnt[buf][j][q]; if (q < warp) before += cq; tot += cq; }
+            int lrank = before + __popc(bal[j] & ((1u << lane) - 1u));
+            if (valid[j]) {
+                if (left[j]) dst[start + run_l + lrank] = e[j];
+                else dst[start + n_left + (base + j * NT - run_l) + (tid - lrank)] = e[j];
+            }
+            run_l += tot;
+        }
+    }
+}
+
+// launchers implemented in f16_tree_random.cu / f16_tree_best.cu
+int f16_launch_build_random(const F16FitParams& P, cudaStream_t st);
+int f16_launch_build_best(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
+int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

@@ -1,0 +1,420 @@
+// ExtraTrees: DepthFirstTreeBuilder + RandomSplitter + Gini, one CTA per tree.
+//   node_split_random      sklearn/tree/_splitter.pyx:507-736
+//   find_min_max / partition_samples(_final)   sklearn/tree/_partitioner.pyx:129-167, :217-279
+//   builder loop           sklearn/tree/_tree.pyx:139-336
+// (reference call site: ExtraTreesClassifier(random_state=0).fit, experiment.py:96,469)
+//
+// Two regimes, switched per node by its row count:
+//   * GLOBAL (n > S): the node's packed row ids live in a per-tree global index array; the CTA
+//     makes three coalesced sweeps with gathers from the L2-resident row matrix - min/max of
+//     all features (one float4 per thread), left-count of the <= 4 candidate thresholds,
+//     stable out-of-place partition (ping-pong by depth parity).
+//   * SHARED (n <= S): the node's rows are copied ONCE into shared memory (column-major,
+//     odd stride => conflict-free) and the whole subtree is grown from there by warp 0 alone:
+//     no block barriers, no global loads, only node records are stored to HBM.  The median
+//     internal node has a few dozen rows, so most nodes of a tree take this path.
+// The xorshift stream, the feature permutation and the node numbering are shared by both
+// regimes, so the tree is identical to the CPU one regardless of where a node is processed.
+// Compile with -fmad=false.
+#include "f16_tree_dev.cuh"
+
+template <int DP> struct SubCfg;
+template <> struct SubCfg<16> { static constexpr int S = 512; };
+template <> struct SubCfg<8> { static constexpr int S = 1024; };
+
+// ------------------------------------------------------------------ SHARED regime (warp 0)
+template <int DP>
+__device__ void subtree_warp(Ctl& c, DrawState& ds, const TreeStack& stk, const F16FitParams& P, F16Node* nodes,
+                             const float* s_col, uint16_t (*s_idx)[SubCfg<DP>::S], const uint8_t* s_y,
+                             int* s_cand_f, double* s_cand_thr) {
+    constexpr int S = SubCfg<DP>::S;
+    constexpr int SP = S + 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const double W_total = (double)P.n;
+    int sp = c.sp, node_count = c.node_count;
+    uint32_t rng = ds.rng;
+    const int d = P.d, max_features = P.max_features;
+
+    while (sp > 0) {
+        F16StackRec r = stk.get(sp - 1);
+        if (!r.pad) break;                      // back to a node that lives in global memory
+        sp--;
+        const int start = r.start, nn = r.end - r.start;
+        const int par = r.depth & 1;
+        const uint16_t* idx = s_idx[par] + start;
+        const int t0 = r.c0, t1 = r.c1;
+        bool split = false;
+        int best_f = -2, n_left = 0, bl0 = 0, bl1 = 0;
+        double best_thr = -2.0;
+        int n_total = r.n_const;
+        uint32_t cmask = r.const_mask;
+
+        if (!leaf_pretest(nn, t0, t1)) {
+            // ---- feature draw; every lane runs the scalar loop on its own copy of the state,
+            //      lane 0 applies the swaps to the shared permutation
+            int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0, ncand = 0;
+            const int n_known = r.n_const;
+            while (f_i > n_total && (n_visited < max_features || n_visited <= n_found + n_drawn)) {
+                n_visited++;
+                int f_j = f16_rand_int(n_drawn, f_i - n_found, &rng);
+                if (f_j < n_known) {
+                    int a = ds.features[n_drawn], b = ds.features[f_j];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[n_drawn] = b; ds.features[f_j] = a; }
+                    __syncwarp();
+                    n_drawn++;
+                    continue;
+                }
+                f_j += n_found;
+                const int f = ds.features[f_j];
+                float mn = INFINITY, mx = -INFINITY;
+                for (int i = lane; i < nn; i += 32) {
+                    float v = s_col[f * SP + idx[i]];
+                    mn = fminf(mn, v); mx = fmaxf(mx, v);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(F16_FULL, mn, off));
+                    mx = fmaxf(mx, __shfl_xor_sync(F16_FULL, mx, off));
+                }
+                if (mx <= __fadd_rn(mn, 1e-7f)) {
+                    int b = ds.features[n_total];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[f_j] = b; ds.features[n_total] = f; }
+                    __syncwarp();
+                    n_found++; n_total++;
+                    continue;
+                }
+                f_i--;
+                {
+                    int b = ds.features[f_i];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[f_i] = f; ds.features[f_j] = b; }
+                    __syncwarp();
+                }
+                double thr = f16_rand_uniform((double)mn, (double)mx, &rng);
+                if (thr == (double)mx) thr = (double)mn;
+                if (lane == 0) { s_cand_f[ncand] = f; s_cand_thr[ncand] = thr; }
+                ncand++;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];
+                for (int i = n_known; i < n_total; i++) ds.const_feats[i] = ds.features[i];
+            }
+            __syncwarp();
+            for (int i = n_known; i < n_total; i++) cmask |= 1u << ds.const_feats[i];
+
+            // ---- evaluate the candidates (strict >, first wins)
+            double best = -INFINITY;
+            for (int k = 0; k < ncand; k++) {
+                const int f = s_cand_f[k];
+                const double thr = s_cand_thr[k];
+                int nl = 0, l1 = 0;
+                for (int base = 0; base < nn; base += 32) {
+                    int i = base + lane;
+                    bool valid = i < nn;
+                    int li = valid ? idx[i] : 0;
+                    bool left = valid && ((double)s_col[f * SP + li] <= thr);
+                    unsigned bal = __ballot_sync(F16_FULL, left);
+                    unsigned by = __ballot_sync(F16_FULL, left && s_y[li]);
+                    nl += __popc(bal); l1 += __popc(by);
+                }
+                double proxy = gini_proxy(nl - l1, l1, t0, t1);
+                if (proxy > best) { best = proxy; best_f = f; best_thr = thr; n_left = nl; bl1 = l1; bl0 = nl - l1; }
+            }
+            if (best_f >= 0) split = improvement_ok(bl0, bl1, t0, t1, W_total);
+        }
+
+        // ---- node record
+        const int id = node_count++;
+        if (id >= P.node_cap || sp + 2 > P.stack_cap) { if (lane == 0) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; } break; }
+        if (lane == 0) {
+            F16Node nd;
+            nd.thr = split ? best_thr : -2.0;
+            nd.feature = split ? best_f : -2;
+            nd.right = -1;
+            nd.c0 = t0; nd.c1 = t1; nd.n = nn; nd.depth = r.depth;
+            nodes[id] = nd;
+            if (r.parent >= 0 && !r.is_left) nodes[r.parent].right = id;
+        }
+        if (split) {
+            // ---- stable partition idx[par] -> idx[par ^ 1]
+            uint16_t* out = s_idx[par ^ 1] + start;
+            int run_l = 0;
+            for (int base = 0; base < nn; base += 32) {
+                int i = base + lane;
+                bool valid = i < nn;
+                int li = valid ? idx[i] : 0;
+                bool left = valid && ((double)s_col[best_f * SP + li] <= best_thr);
+                unsigned bal = __ballot_sync(F16_FULL, left);
+                int lrank = __popc(bal & lt);
+                if (valid) {
+                    if (left) out[run_l + lrank] = (uint16_t)li;
+                    else out[n_left + (base - run_l) + (lane - lrank)] = (uint16_t)li;
+                }
+                run_l += __popc(bal);
+            }
+            if (lane == 0) {
+                F16StackRec q;
+                q.parent = id; q.depth = r.depth + 1; q.n_const = (int16_t)n_total; q.const_mask = cmask; q.pad = 1;
+                q.start = start + n_left; q.end = r.end; q.c0 = t0 - bl0; q.c1 = t1 - bl1; q.is_left = 0;
+                stk.put(sp, q);
+                q.start = start; q.end = start + n_left; q.c0 = bl0; q.c1 = bl1; q.is_left = 1;
+                stk.put(sp + 1, q);
+            }
+            sp += 2;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { c.sp = sp; c.node_count = node_count; ds.rng = rng; }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int DP>
+__global__ void __launch_bounds__(NT, 4) k_build_random(F16FitParams P) {
+    constexpr int Q = DP / 4;
+    constexpr int SPI = NT / Q;
+    constexpr int S = SubCfg<DP>::S;
+    constexpr int SP = S + 1;
+    __shared__ Ctl c;
+    __shared__ DrawState ds;
+    __shared__ F16StackRec s_stack[SSTK];
+    __shared__ float s_min[F16_MAX_D], s_max[F16_MAX_D];
+    __shared__ float s_wmin[NW][F16_MAX_D], s_wmax[NW][F16_MAX_D];
+    __shared__ int s_cand_f[F16_MAX_D];
+    __shared__ double s_cand_thr[F16_MAX_D];
+    __shared__ unsigned long long s_part[NW][4];
+    __shared__ unsigned long long s_cnt[F16_MAX_D];
+    __shared__ int s_wcnt[2][PU][NW];
+    __shared__ float s_col[DP * SP];
+    __shared__ uint16_t s_idx[2][S];
+    __shared__ uint8_t s_y[S];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x;
+    const int n = P.n;
+    const float* __restrict__ X = P.X;
+    uint32_t* buf0 = P.buf + (size_t)t * 2 * n;
+    uint32_t* buf1 = buf0 + n;
+    F16Node* nodes = P.nodes + (size_t)t * P.node_cap;
+    TreeStack stk;
+    stk.smem = s_stack;
+    stk.gmem = P.stack + (size_t)t * P.stack_cap;
+    const double W_total = (double)n;
+
+    // ---- root: identity sample list with packed labels; class counts
+    unsigned long long cnt = 0;
+    for (int i = tid; i < n; i += NT) {
+        uint32_t y = P.y[i];
+        buf0[i] = f16_pack((uint32_t)i, 1u, y);
+        cnt += y ? (1ull << 32) : 1ull;
+    }
+    cnt = f16_warp_sum_u64(cnt);
+    if (lane == 0) s_part[warp][0] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int q = 0; q < NW; q++) tot += s_part[q][0];
+        for (int f = 0; f < F16_MAX_D; f++) { ds.features[f] = f; ds.const_feats[f] = 0; }
+        ds.rng = P.rand_r_state[t];
+        F16StackRec r;
+        r.start = 0; r.end = n; r.parent = -1; r.c0 = (int)(uint32_t)tot; r.c1 = (int)(tot >> 32);
+        r.const_mask = 0; r.n_const = 0; r.is_left = 0; r.pad = 0; r.depth = 0;
+        c.sp = 0; c.node_count = 0; c.done = 0;
+        stk.put(c.sp++, r);
+    }
+    __syncthreads();
+
+    while (true) {
+        if (tid == 0) pop_node(c, stk);
+        __syncthreads();
+        if (c.done) break;
+        const int start = c.start, nn = c.end - c.start;
+        const uint32_t* src = (c.depth & 1) ? buf1 : buf0;
+        uint32_t* dst = (c.depth & 1) ? buf0 : buf1;
+
+        if (!c.leaf && nn <= S) {
+            // ================= SHARED regime: relocate the node, grow its whole subtree
+            {
+                const int q = tid % Q;
+                for (int i = tid / Q; i < nn; i += SPI) {
+                    uint32_t e = src[start + i];
+                    float4 v = __ldg(reinterpret_cast<const float4*>(X + (size_t)f16_id(e) * DP) + q);
+                    s_col[(q * 4 + 0) * SP + i] = v.x;
+                    s_col[(q * 4 + 1) * SP + i] = v.y;
+                    s_col[(q * 4 + 2) * SP + i] = v.z;
+                    s_col[(q * 4 + 3) * SP + i] = v.w;
+                    if (q == 0) { s_idx[c.depth & 1][i] = (uint16_t)i; s_y[i] = (uint8_t)f16_y(e); }
+                }
+            }
+            if (tid == 0) {
+                F16StackRec r;
+                r.start = 0; r.end = nn; r.parent = c.parent; r.c0 = c.c0; r.c1 = c.c1;
+                r.const_mask = c.const_mask; r.n_const = (int16_t)c.n_const; r.is_left = (uint8_t)c.is_left;
+                r.pad = 1; r.depth = c.depth;
+                stk.put(c.sp++, r);
+            }
+            __syncthreads();
+            if (warp == 0) subtree_warp<DP>(c, ds, stk, P, nodes, s_col, s_idx, s_y, s_cand_f, s_cand_thr);
+            __syncthreads();
+            if (c.done) break;
+            continue;
+        }
+
+        // ================= GLOBAL regime
+        if (!c.leaf) {
+            // ---- pass 1: min / max of every feature over the node's rows
+            {
+                const int q = tid % Q, sl = tid / Q;
+                float mn[4], mx[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+                for (int i0 = sl; i0 < nn; i0 += SPI * 4) {
+                    uint32_t id[4]; float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { int i = i0 + u * SPI; id[u] = f16_id(src[start + (i < nn ? i : i0)]); }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)id[u] * DP) + q);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {     // tail slots re-read row i0: harmless for min/max
+                        mn[0] = fminf(mn[0], v[u].x); mx[0] = fmaxf(mx[0], v[u].x);
+                        mn[1] = fminf(mn[1], v[u].y); mx[1] = fmaxf(mx[1], v[u].y);
+                        mn[2] = fminf(mn[2], v[u].z); mx[2] = fmaxf(mx[2], v[u].z);
+                        mn[3] = fminf(mn[3], v[u].w); mx[3] = fmaxf(mx[3], v[u].w);
+                    }
+                }
+#pragma unroll
+                for (int off = Q; off < 32; off <<= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        mn[j] = fminf(mn[j], __shfl_xor_sync(F16_FULL, mn[j], off));
+                        mx[j] = fmaxf(mx[j], __shfl_xor_sync(F16_FULL, mx[j], off));
+                    }
+                }
+                if (lane < Q) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { s_wmin[warp][lane * 4 + j] = mn[j]; s_wmax[warp][lane * 4 + j] = mx[j]; }
+                }
+                __syncthreads();
+                if (tid < DP) {
+                    float a = s_wmin[0][tid], b = s_wmax[0][tid];
+#pragma unroll
+                    for (int q2 = 1; q2 < NW; q2++) { a = fminf(a, s_wmin[q2][tid]); b = fmaxf(b, s_wmax[q2][tid]); }
+                    s_min[tid] = a; s_max[tid] = b;
+                }
+                __syncthreads();
+            }
+            // ---- draw features + thresholds (thread 0; scalar xorshift stream)
+            if (tid == 0) {
+                const int d = P.d, max_features = P.max_features;
+                int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
+                const int n_known = c.n_const;
+                int n_total = n_known, ncand = 0;
+                while (f_i > n_total && (n_visited < max_features || n_visited <= n_found + n_drawn)) {
+                    n_visited++;
+                    int f_j = f16_rand_int(n_drawn, f_i - n_found, &ds.rng);
+                    if (f_j < n_known) {
+                        int tmp = ds.features[n_drawn]; ds.features[n_drawn] = ds.features[f_j]; ds.features[f_j] = tmp;
+                        n_drawn++;
+                        continue;
+                    }
+                    f_j += n_found;
+                    int f = ds.features[f_j];
+                    float mn = s_min[f], mx = s_max[f];
+                    if (mx <= __fadd_rn(mn, 1e-7f)) {
+                        ds.features[f_j] = ds.features[n_total]; ds.features[n_total] = f;
+                        n_found++; n_total++;
+                        continue;
+                    }
+                    f_i--;
+                    { int tmp = ds.features[f_i]; ds.features[f_i] = ds.features[f_j]; ds.features[f_j] = tmp; }
+                    double thr = f16_rand_uniform((double)mn, (double)mx, &ds.rng);
+                    if (thr == (double)mx) thr = (double)mn;
+                    s_cand_f[ncand] = f; s_cand_thr[ncand] = thr; ncand++;
+                }
+                for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];
+                uint32_t m = c.const_mask;
+                for (int i = n_known; i < n_total; i++) { ds.const_feats[i] = ds.features[i]; m |= 1u << ds.features[i]; }
+                c.ncand = ncand; c.n_const_out = n_total; c.const_mask_out = m;
+            }
+            __syncthreads();
+            const int ncand = c.ncand;
+            if (ncand > 0) {
+                // ---- pass 2: left counts of every candidate threshold (4 candidates per sweep)
+                for (int k0 = 0; k0 < ncand; k0 += 4) {
+                    int fk[4]; double tk[4];
+                    unsigned long long acc[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int k = (k0 + j < ncand) ? k0 + j : k0;
+                        fk[j] = s_cand_f[k]; tk[j] = s_cand_thr[k]; acc[j] = 0;
+                    }
+                    for (int i0 = tid; i0 < nn; i0 += NT * 2) {
+                        const int i1 = i0 + NT;
+                        const bool v1 = i1 < nn;
+                        uint32_t e0 = src[start + i0], e1 = v1 ? src[start + i1] : 0u;
+                        const float* r0 = X + (size_t)f16_id(e0) * DP;
+                        const float* r1 = X + (size_t)f16_id(e1) * DP;
+                        float a[4], b[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { a[j] = __ldg(r0 + fk[j]); b[j] = __ldg(r1 + fk[j]); }
+                        unsigned long long one0 = 1ull | ((unsigned long long)f16_y(e0) << 32);
+                        unsigned long long one1 = v1 ? (1ull | ((unsigned long long)f16_y(e1) << 32)) : 0ull;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if ((double)a[j] <= tk[j]) acc[j] += one0;
+                            if ((double)b[j] <= tk[j]) acc[j] += one1;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[j] = f16_warp_sum_u64(acc[j]);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) s_part[warp][j] = acc[j];
+                    }
+                    __syncthreads();
+                    if (tid < 4 && k0 + tid < ncand) {
+                        unsigned long long s = 0;
+                        for (int q2 = 0; q2 < NW; q2++) s += s_part[q2][tid];
+                        s_cnt[k0 + tid] = s;
+                    }
+                    __syncthreads();
+                }
+                // ---- choose the best candidate (strict >, first wins)
+                if (tid == 0) {
+                    double best = -INFINITY; int bk = -1;
+                    for (int k = 0; k < ncand; k++) {
+                        int nl = (int)(uint32_t)s_cnt[k], l1 = (int)(s_cnt[k] >> 32), l0 = nl - l1;
+                        double proxy = gini_proxy(l0, l1, c.c0, c.c1);
+                        if (proxy > best) { best = proxy; bk = k; }
+                    }
+                    if (bk >= 0) {
+                        int nl = (int)(uint32_t)s_cnt[bk], l1 = (int)(s_cnt[bk] >> 32), l0 = nl - l1;
+                        c.best_f = s_cand_f[bk]; c.best_thr = s_cand_thr[bk];
+                        c.n_left = nl; c.l0 = l0; c.l1 = l1;
+                        c.split = improvement_ok(l0, l1, c.c0, c.c1, W_total) ? 1 : 0;
+                    }
+                }
+            }
+        }
+        if (tid == 0) finish_node(c, P, nodes, stk);
+        __syncthreads();
+        if (c.done) break;
+        if (c.split) {
+            const int bf = c.best_f; const double bthr = c.best_thr;
+            block_partition(src, dst, start, nn, c.n_left,
+                            [&](uint32_t e) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
+            __syncthreads();
+        }
+    }
+    if (tid == 0) P.node_count[t] = c.node_count;
+}
+
+int f16_launch_build_random(const F16FitParams& P, cudaStream_t st) {
+    if (P.dp == 8) k_build_random<8><<<P.n_trees, NT, 0, st>>>(P);
+    else k_build_random<16><<<P.n_trees, NT, 0, st>>>(P);
+    f16_count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? F16_OK : F16_ERR_CUDA;
+}

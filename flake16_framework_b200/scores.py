@@ -131,7 +131,7 @@ def _minority_clean_mask(counts, strategy):
     return 0b11 & ~(1 << minority)
 
 
-def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers):
+def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers, model_streams):
     """One (dataset, fold): stage, resample per balancing, fit/predict/count per model."""
     ds_key, fold = unit
     ft = ds_key[0]
@@ -149,6 +149,7 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers)
     minority = 0 if counts[0] <= counts[1] else 1
 
     cache = {}
+    keep = []      # tensors read by side streams stay referenced until the unit is done
 
     def nn4(tag, X):
         if tag not in cache:
@@ -195,18 +196,30 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers)
         sorted_idx = None
         if any(m != "Extra Trees" for m in models):
             sorted_idx = ops.argsort_columns(Xrow, d)
+        # the three models of a resample are independent: fork them onto side streams so the
+        # single-CTA DecisionTree does not serialise behind the forests (and the next
+        # balancing's k-NN overlaps with these fits)
+        keep.append((Xrow, yb, sorted_idx))
+        ready = torch.cuda.Event()
+        ready.record()
         for model in MODELS:
             if model not in models:
                 continue
             ci = cfg_index[ds_key + (bal, model)]
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record()
-            forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx)
-            e1.record()
-            pred = forest.predict(Xte)
-            e2.record()
-            ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
+            side = model_streams[model]
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx)
+                e1.record()
+                pred = forest.predict(Xte)
+                e2.record()
+                ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
+                keep.append(pred)
             timers.append((ci, e0, e1, e2, forest))
+    for side in model_streams.values():
+        side.synchronize()
     return n_tr
 
 
@@ -252,6 +265,7 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
     def worker():
         torch.cuda.set_device(device)
         stream = torch.cuda.Stream(device=device)
+        model_streams = {m: torch.cuda.Stream(device=device) for m in MODELS}
         timers = []
         try:
             with torch.cuda.stream(stream):
@@ -260,7 +274,7 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
                         u = q.get_nowait()
                     except queue.Empty:
                         break
-                    _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers)
+                    _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers, model_streams)
                     stream.synchronize()
                     for ci, e0, e1, e2, forest in timers:
                         forest.status()
