@@ -11,17 +11,33 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libf16_b200.so")
+LIB_PATH = os.environ.get("F16_LIB") or os.path.join(_HERE, "libf16_b200.so")
 
-# (source, extra flags).  -fmad=false wherever float64 expressions must round like the CPU.
-_SOURCES = (
-    ("f16_tree.cu", ["-fmad=false"]),
-    ("f16_tree_random.cu", ["-fmad=false"]),
-    ("f16_tree_best.cu", ["-fmad=false"]),
-    ("f16_misc.cu", ["-fmad=false"]),
-    ("f16_sort.cu", []),
-    ("f16_knn.cu", []),
-)
+# Tree-kernel tunables (threads per tree CTA, min CTAs/SM, rows of the shared-memory regime).
+TUNE = {"ET_NT": 256, "ET_MINB": 4, "ET_S16": 512, "ET_S8": 1024,
+        "RF_NT": 256, "RF_MINB": 3, "DT_NT": 256, "DT_MINB": 1}
+
+
+def _sources(tune):
+    """(source, object tag, extra flags).  -fmad=false wherever float64 expressions must
+    round like the CPU.  The tree builders are compiled once per variant (ET / RF / DT)."""
+    t = dict(TUNE)
+    t.update(tune or {})
+    return (
+        ("f16_tree.cu", "", ["-fmad=false"]),
+        ("f16_tree_random.cu", "_et", ["-fmad=false", "-DF16_VARIANT=_et", "-DNT=%d" % t["ET_NT"],
+                                        "-DF16_MINB=%d" % t["ET_MINB"], "-DF16_S16=%d" % t["ET_S16"],
+                                        "-DF16_S8=%d" % t["ET_S8"]]),
+        ("f16_tree_best.cu", "_rf", ["-fmad=false", "-DF16_VARIANT=_rf", "-DNT=%d" % t["RF_NT"],
+                                      "-DF16_MINB=%d" % t["RF_MINB"], "-DF16_WITH_BOOTSTRAP"]),
+        ("f16_tree_best.cu", "_dt", ["-fmad=false", "-DF16_VARIANT=_dt", "-DNT=%d" % t["DT_NT"],
+                                      "-DF16_MINB=%d" % t["DT_MINB"]]),
+        ("f16_misc.cu", "", ["-fmad=false"]),
+        ("f16_sort.cu", "", []),
+        ("f16_knn.cu", "", []),
+    )
+
+
 _ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -29,17 +45,21 @@ def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
-def build(force=False, verbose=False):
-    """Compiles every CUDA source for sm_100a and links libf16_b200.so in-tree."""
+def build(force=False, verbose=False, tune=None, out=None):
+    """Compiles every CUDA source for sm_100a and links libf16_b200.so in-tree.
+    ``tune`` / ``out`` build an experimental variant under another name (tools/tune_*.py)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     hdrs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
     objs, rebuilt = [], False
     procs = []
-    for src, extra in _SOURCES:
+    tag = "" if out is None else "." + os.path.basename(out).replace(".so", "")
+    force = force or out is not None
+    lib_path = out or os.path.join(_HERE, "libf16_b200.so")
+    for src, variant, extra in _sources(tune):
         s = os.path.join(_CSRC, src)
-        o = os.path.join(_CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(_CSRC, src.replace(".cu", variant + tag + ".o"))
         objs.append(o)
-        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs):
+        if force or _newer(s, o) or any(_newer(h, o) for h in hdrs) or _newer(__file__, o):
             cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *_ARCH, "-Xcompiler", "-fPIC",
                    "-Xptxas", "-v" if verbose else "-O3", *extra, "-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -50,10 +70,13 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out.decode()))
         if verbose:
             sys.stderr.write(out.decode())
-    if rebuilt or not os.path.exists(LIB_PATH):
-        cmd = [nvcc, "-shared", *_ARCH, "-o", LIB_PATH, *objs, "-lcudart"]
+    if rebuilt or not os.path.exists(lib_path):
+        cmd = [nvcc, "-shared", *_ARCH, "-o", lib_path, *objs, "-lcudart"]
         subprocess.check_call(cmd)
-    return LIB_PATH
+    if out is not None:
+        for o in objs:
+            os.remove(o)
+    return lib_path
 
 
 _lib = None
@@ -83,7 +106,7 @@ SIGNATURES = {
     "f16_forest_node_counts": ([c_void_p, c_void_p, c_void_p], c_int),
     "f16_forest_export": ([c_void_p, c_int32, c_int64] + [c_void_p] * 8 + [c_void_p], c_int),
     "f16_forest_free": ([c_void_p, c_void_p], None),
-    "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p], c_int),
+    "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p], c_int),
     "f16_smote_generate": ([c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p], c_int),
     "f16_tomek_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),

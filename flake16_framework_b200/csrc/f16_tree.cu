@@ -172,7 +172,8 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
         F->has_ev = 1;
         CUDA_TRY(cudaEventRecord(F->ev0, st));
     }
-    rc = best ? f16_launch_build_best(P, dyn, st) : f16_launch_build_random(P, st);
+    rc = (kind == F16_KIND_ET) ? f16_launch_build_random_et(P, st)
+       : (kind == F16_KIND_RF) ? f16_launch_build_best_rf(P, dyn, st) : f16_launch_build_best_dt(P, dyn, st);
     if (rc) { f16_set_error("tree build kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     if (F->has_ev) CUDA_TRY(cudaEventRecord(F->ev1, st));
     CUDA_TRY(cudaFreeAsync(P.buf, st));

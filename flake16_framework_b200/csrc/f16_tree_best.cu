@@ -21,15 +21,18 @@
 // Compile with -fmad=false.
 #include "f16_tree_dev.cuh"
 
+#ifdef F16_WITH_BOOTSTRAP
+#define BNT 256
+#define BNW 8
 // ------------------------------------------------------------------ bootstrap (RF)
 // One CTA per tree: MT19937(tree_seed).randint(0, n, n) -> bincount, entirely on device.
 // The 624-word state block is regenerated in three dependency-free phases.
-__global__ void __launch_bounds__(NT) k_bootstrap(const uint32_t* __restrict__ tree_seed, int n,
+__global__ void __launch_bounds__(BNT) k_bootstrap(const uint32_t* __restrict__ tree_seed, int n,
                                                  uint32_t* __restrict__ w32 /*[n_trees][ceil(n/4)]*/,
                                                  int words_per_tree) {
     __shared__ uint32_t mt[624];
     __shared__ uint32_t out[624];
-    __shared__ int s_wsum[2][NW];
+    __shared__ int s_wsum[2][BNW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* w = w32 + (size_t)blockIdx.x * words_per_tree;
     if (tid == 0) {
@@ -56,10 +59,10 @@ __global__ void __launch_bounds__(NT) k_bootstrap(const uint32_t* __restrict__ t
         __syncthreads();
         if (tid < 170) mt[tid + 454] = c ^ f16_mt_twist(a, b);
         __syncthreads();
-        for (int i = tid; i < 624; i += NT) out[i] = f16_mt_temper(mt[i]) & mask;
+        for (int i = tid; i < 624; i += BNT) out[i] = f16_mt_temper(mt[i]) & mask;
         __syncthreads();
         // ---- ordered acceptance: only the first (n - produced) accepted draws count
-        for (int base = 0; base < 624 && produced < n; base += NT, buf ^= 1) {
+        for (int base = 0; base < 624 && produced < n; base += BNT, buf ^= 1) {
             int i = base + tid;
             uint32_t v = (i < 624) ? out[i] : 0xffffffffu;
             bool acc = (i < 624) && (v <= rng);
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(NT) k_bootstrap(const uint32_t* __restrict__ t
             if (lane == 0) s_wsum[buf][warp] = __popc(bal);
             __syncthreads();
             int before = 0, tot = 0;
-            for (int q = 0; q < NW; q++) { int cq = s_wsum[buf][q]; if (q < warp) before += cq; tot += cq; }
+            for (int q = 0; q < BNW; q++) { int cq = s_wsum[buf][q]; if (q < warp) before += cq; tot += cq; }
             int rank = produced + before + __popc(bal & ((1u << lane) - 1u));
             if (acc && rank < n) atomicAdd(&w[v >> 2], 1u << ((v & 3u) * 8u));
             produced += tot;
@@ -77,12 +80,15 @@ __global__ void __launch_bounds__(NT) k_bootstrap(const uint32_t* __restrict__ t
 }
 
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st) {
-    k_bootstrap<<<n_trees, NT, 0, st>>>(seeds_dev, n, w32, words_per_tree);
+    k_bootstrap<<<n_trees, BNT, 0, st>>>(seeds_dev, n, w32, words_per_tree);
     f16_count_launch(1);
     return cudaGetLastError() == cudaSuccess ? F16_OK : F16_ERR_CUDA;
 }
 
+#endif
+
 // ------------------------------------------------------------------ best splitter
+#define k_build_best F16_CAT(k_build_best, F16_VARIANT)
 struct BestCand {
     double proxy;
     unsigned long long key;   // (visit order k << 32) | position p ; smaller wins ties
@@ -124,7 +130,7 @@ __device__ __forceinline__ void warp_partition(const uint32_t* src, uint32_t* ds
 }
 
 template <int DP>
-__global__ void __launch_bounds__(NT, 3) k_build_best(F16FitParams P) {
+__global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
     extern __shared__ uint32_t s_side_dyn[];
     __shared__ Ctl c;
     __shared__ DrawState ds;
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(NT, 3) k_build_best(F16FitParams P) {
     if (tid == 0) P.node_count[t] = c.node_count;
 }
 
-int f16_launch_build_best(const F16FitParams& P, size_t dyn_smem, cudaStream_t st) {
+int F16_CAT(f16_launch_build_best, F16_VARIANT)(const F16FitParams& P, size_t dyn_smem, cudaStream_t st) {
     cudaError_t e;
     if (P.dp == 8) {
         e = cudaFuncSetAttribute(k_build_best<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * F16_SIDE_SMEM_MAX_WORDS);

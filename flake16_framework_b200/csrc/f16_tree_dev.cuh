@@ -3,7 +3,20 @@
 #include "f16_tree.cuh"
 #include <math.h>
 
+// Threads per tree-building CTA and the kernel-name suffix are set per compiled variant
+// (-DNT=.. -DF16_VARIANT=..): ExtraTrees / RandomForest trees are plentiful, so they use small
+// CTAs (many trees resident per SM); the single DecisionTree uses a wide one.
+#ifndef NT
 #define NT 256
+#endif
+#ifndef F16_VARIANT
+#define F16_VARIANT _v
+#endif
+#ifndef F16_MINB
+#define F16_MINB 3
+#endif
+#define F16_CAT_(a, b) a##b
+#define F16_CAT(a, b) F16_CAT_(a, b)
 #define NW (NT / 32)
 #define F16_EPS 2.220446049250313e-16
 #define SSTK 64     // stack records cached in shared memory (deeper ones spill to global)
@@ -152,6 +165,7 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
 }
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
-int f16_launch_build_random(const F16FitParams& P, cudaStream_t st);
-int f16_launch_build_best(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
+int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);
+int f16_launch_build_best_rf(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
+int f16_launch_build_best_dt(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

@@ -17,10 +17,18 @@
 // regimes, so the tree is identical to the CPU one regardless of where a node is processed.
 // Compile with -fmad=false.
 #include "f16_tree_dev.cuh"
+#include "f16_tree_random_sub.cuh"
 
 template <int DP> struct SubCfg;
-template <> struct SubCfg<16> { static constexpr int S = 512; };
-template <> struct SubCfg<8> { static constexpr int S = 1024; };
+#ifndef F16_S16
+#define F16_S16 512
+#endif
+#ifndef F16_S8
+#define F16_S8 1024
+#endif
+template <> struct SubCfg<16> { static constexpr int S = F16_S16; };
+template <> struct SubCfg<8> { static constexpr int S = F16_S8; };
+#define k_build_random F16_CAT(k_build_random, F16_VARIANT)
 
 // ------------------------------------------------------------------ SHARED regime (warp 0)
 template <int DP>
@@ -173,7 +181,7 @@ __device__ void subtree_warp(Ctl& c, DrawState& ds, const TreeStack& stk, const 
 
 // ------------------------------------------------------------------ kernel
 template <int DP>
-__global__ void __launch_bounds__(NT, 4) k_build_random(F16FitParams P) {
+__global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     constexpr int Q = DP / 4;
     constexpr int SPI = NT / Q;
     constexpr int S = SubCfg<DP>::S;
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(NT, 4) k_build_random(F16FitParams P) {
                 stk.put(c.sp++, r);
             }
             __syncthreads();
-            if (warp == 0) subtree_warp<DP>(c, ds, stk, P, nodes, s_col, s_idx, s_y, s_cand_f, s_cand_thr);
+            if (warp == 0) subtree_warp_v2<DP, S>(c, ds, stk, P, nodes, s_col, s_idx, s_y);
             __syncthreads();
             if (c.done) break;
             continue;
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(NT, 4) k_build_random(F16FitParams P) {
     if (tid == 0) P.node_count[t] = c.node_count;
 }
 
-int f16_launch_build_random(const F16FitParams& P, cudaStream_t st) {
+int F16_CAT(f16_launch_build_random, F16_VARIANT)(const F16FitParams& P, cudaStream_t st) {
     if (P.dp == 8) k_build_random<8><<<P.n_trees, NT, 0, st>>>(P);
     else k_build_random<16><<<P.n_trees, NT, 0, st>>>(P);
     f16_count_launch(1);

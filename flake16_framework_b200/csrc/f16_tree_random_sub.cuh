@@ -1,0 +1,210 @@
+// SHARED regime of the ExtraTrees builder: one warp grows a whole subtree out of shared memory.
+//
+// The per-node dependency chain is what bounds a tree (its nodes are sequential), so every step
+// is laid out to be short rather than wide:
+//   * min/max of ALL features in one sweep: lane = (feature, row group), so the scalar feature
+//     draw afterwards only shuffles constants out of registers (no data pass per drawn feature);
+//   * the <= 4 candidate thresholds are counted in one sweep (lane = row, 5 ballots per 32 rows);
+//   * the float64 Gini proxies of the candidates and the three Gini terms of the improvement test
+//     are evaluated on different lanes at once (same operations, same rounding as the CPU's
+//     sequential evaluation - only the schedule differs);
+//   * stack, feature permutation and node counter stay in shared memory / registers.
+#pragma once
+#include "f16_tree_dev.cuh"
+
+template <int DP, int S>
+__device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, const F16FitParams& P, F16Node* nodes,
+                                const float* s_col, uint16_t (*s_idx)[S], const uint8_t* s_y) {
+    constexpr int SP = S + 1;
+    constexpr int G = 32 / DP;               // row groups of the all-feature min/max sweep
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const double W_total = (double)P.n;
+    int sp = c.sp, node_count = c.node_count;
+    uint32_t rng = ds.rng;
+    const int d = P.d, max_features = P.max_features;
+    const int mf = lane % DP, mg = lane / DP;
+
+    while (sp > 0) {
+        F16StackRec r = stk.get(sp - 1);
+        if (!r.pad) break;                      // back to a node that lives in global memory
+        sp--;
+        const int start = r.start, nn = r.end - r.start;
+        const int par = r.depth & 1;
+        const uint16_t* idx = s_idx[par] + start;
+        const int t0 = r.c0, t1 = r.c1;
+        bool split = false;
+        int best_f = -2, n_left = 0, bl0 = 0, bl1 = 0;
+        double best_thr = -2.0;
+        int n_total = r.n_const;
+        uint32_t cmask = r.const_mask;
+
+        if (!leaf_pretest(nn, t0, t1)) {
+            // ---- (a) min / max of every feature: lane owns feature mf, row group mg
+            float mn = INFINITY, mx = -INFINITY;
+            {
+                const float* col = s_col + mf * SP;
+                int i = mg;
+                for (; i + 3 * G < nn; i += 4 * G) {
+                    float v0 = col[idx[i]], v1 = col[idx[i + G]], v2 = col[idx[i + 2 * G]], v3 = col[idx[i + 3 * G]];
+                    mn = fminf(fminf(mn, v0), fminf(v1, fminf(v2, v3)));
+                    mx = fmaxf(fmaxf(mx, v0), fmaxf(v1, fmaxf(v2, v3)));
+                }
+                for (; i < nn; i += G) { float v = col[idx[i]]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+                for (int off = DP; off < 32; off <<= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(F16_FULL, mn, off));
+                    mx = fmaxf(mx, __shfl_xor_sync(F16_FULL, mx, off));
+                }
+            }
+            // ---- (b) feature draw (every lane runs the scalar loop on its own copy of the
+            //      state; lane 0 applies the swaps to the shared permutation), candidates are
+            //      evaluated four at a time
+            int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0, ncand = 0;
+            const int n_known = r.n_const;
+            int cf[4] = {0, 0, 0, 0};
+            double ct[4] = {0.0, 0.0, 0.0, 0.0};
+            double best = -INFINITY;
+
+            auto eval_chunk = [&](int cnt) {
+                int nl[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0};
+                for (int base = 0; base < nn; base += 32) {
+                    const int i = base + lane;
+                    const bool valid = i < nn;
+                    const int li = valid ? idx[i] : 0;
+                    const unsigned ym = __ballot_sync(F16_FULL, valid && s_y[li]);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k < cnt) {
+                            bool left = valid && ((double)s_col[cf[k] * SP + li] <= ct[k]);
+                            unsigned bal = __ballot_sync(F16_FULL, left);
+                            nl[k] += __popc(bal); l1[k] += __popc(bal & ym);
+                        }
+                    }
+                }
+                // proxies: lane 2k -> (-w_R * g_R), lane 2k+1 -> (w_L * g_L) of candidate k
+                const int k = (lane >> 1) & 3;
+                int mnl = nl[0], ml1 = l1[0];
+#pragma unroll
+                for (int j = 1; j < 4; j++) if (k == j) { mnl = nl[j]; ml1 = l1[j]; }
+                double a, b, part;
+                if (lane & 1) { a = (double)(mnl - ml1); b = (double)ml1; double w = a + b; part = w * gini_of(a, b, w); }
+                else { a = (double)(t0 - (mnl - ml1)); b = (double)(t1 - ml1); double w = a + b; part = (-w) * gini_of(a, b, w); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < cnt) {
+                        double proxy = __shfl_sync(F16_FULL, part, 2 * j) - __shfl_sync(F16_FULL, part, 2 * j + 1);
+                        if (proxy > best) {
+                            best = proxy; best_f = cf[j]; best_thr = ct[j]; n_left = nl[j]; bl1 = l1[j]; bl0 = nl[j] - l1[j];
+                        }
+                    }
+                }
+            };
+
+            while (f_i > n_total && (n_visited < max_features || n_visited <= n_found + n_drawn)) {
+                n_visited++;
+                int f_j = f16_rand_int(n_drawn, f_i - n_found, &rng);
+                if (f_j < n_known) {
+                    int a = ds.features[n_drawn], b = ds.features[f_j];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[n_drawn] = b; ds.features[f_j] = a; }
+                    __syncwarp();
+                    n_drawn++;
+                    continue;
+                }
+                f_j += n_found;
+                const int f = ds.features[f_j];
+                const float fmn = __shfl_sync(F16_FULL, mn, f), fmx = __shfl_sync(F16_FULL, mx, f);
+                if (fmx <= __fadd_rn(fmn, 1e-7f)) {
+                    int b = ds.features[n_total];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[f_j] = b; ds.features[n_total] = f; }
+                    __syncwarp();
+                    n_found++; n_total++;
+                    continue;
+                }
+                f_i--;
+                {
+                    int b = ds.features[f_i];
+                    __syncwarp();
+                    if (lane == 0) { ds.features[f_i] = f; ds.features[f_j] = b; }
+                    __syncwarp();
+                }
+                double thr = f16_rand_uniform((double)fmn, (double)fmx, &rng);
+                if (thr == (double)fmx) thr = (double)fmn;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (j == ncand) { cf[j] = f; ct[j] = thr; }
+                ncand++;
+                if (ncand == 4) { eval_chunk(4); ncand = 0; }
+            }
+            if (ncand > 0) eval_chunk(ncand);
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];
+                for (int i = n_known; i < n_total; i++) ds.const_feats[i] = ds.features[i];
+            }
+            __syncwarp();
+            for (int i = n_known; i < n_total; i++) cmask |= 1u << ds.const_feats[i];
+
+            // ---- (c) improvement test: lane 0 parent term, lane 1 right term, lane 2 left term
+            if (best_f >= 0) {
+                const int role = lane % 3;
+                double a, b, num, den;
+                const double wn = (double)t0 + (double)t1;
+                if (role == 0) { a = (double)t0; b = (double)t1; num = wn; den = W_total; }
+                else if (role == 1) { a = (double)(t0 - bl0); b = (double)(t1 - bl1); num = a + b; den = wn; }
+                else { a = (double)bl0; b = (double)bl1; num = a + b; den = wn; }
+                const double g = gini_of(a, b, a + b);
+                const double ratio = num / den;
+                const double prod = ratio * g;
+                const double imp = __shfl_sync(F16_FULL, g, 0), A = __shfl_sync(F16_FULL, ratio, 0);
+                const double B = __shfl_sync(F16_FULL, prod, 1), C = __shfl_sync(F16_FULL, prod, 2);
+                const double improvement = A * (imp - B - C);
+                split = !(improvement + F16_EPS < 0.0);
+            }
+        }
+
+        // ---- node record
+        const int id = node_count++;
+        if (id >= P.node_cap || sp + 2 > P.stack_cap) { if (lane == 0) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; } break; }
+        if (lane == 0) {
+            F16Node nd;
+            nd.thr = split ? best_thr : -2.0;
+            nd.feature = split ? best_f : -2;
+            nd.right = -1;
+            nd.c0 = t0; nd.c1 = t1; nd.n = nn; nd.depth = r.depth;
+            nodes[id] = nd;
+            if (r.parent >= 0 && !r.is_left) nodes[r.parent].right = id;
+        }
+        if (split) {
+            // ---- stable partition idx[par] -> idx[par ^ 1]
+            uint16_t* out = s_idx[par ^ 1] + start;
+            const float* col = s_col + best_f * SP;
+            int run_l = 0;
+            for (int base = 0; base < nn; base += 32) {
+                int i = base + lane;
+                bool valid = i < nn;
+                int li = valid ? idx[i] : 0;
+                bool left = valid && ((double)col[li] <= best_thr);
+                unsigned bal = __ballot_sync(F16_FULL, left);
+                int lrank = __popc(bal & lt);
+                if (valid) {
+                    if (left) out[run_l + lrank] = (uint16_t)li;
+                    else out[n_left + (base - run_l) + (lane - lrank)] = (uint16_t)li;
+                }
+                run_l += __popc(bal);
+            }
+            if (lane == 0) {
+                F16StackRec q;
+                q.parent = id; q.depth = r.depth + 1; q.n_const = (int16_t)n_total; q.const_mask = cmask; q.pad = 1;
+                q.start = start + n_left; q.end = r.end; q.c0 = t0 - bl0; q.c1 = t1 - bl1; q.is_left = 0;
+                stk.put(sp, q);
+                q.start = start; q.end = start + n_left; q.c0 = bl0; q.c1 = bl1; q.is_left = 1;
+                stk.put(sp + 1, q);
+            }
+            sp += 2;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { c.sp = sp; c.node_count = node_count; ds.rng = rng; }
+}

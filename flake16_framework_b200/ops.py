@@ -6,6 +6,7 @@ back: a missing library or a failing call raises ``F16Error``.
 """
 
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -171,11 +172,41 @@ def forest_fit(Xrow, y, d, kind, n_estimators=100, seed=0, sorted_idx=None, max_
 
 
 # ----------------------------------------------------------------------------- k-NN + samplers
-def knn(A, Q, k):
+_COL_ORDER = threading.local()
+
+
+class column_order:
+    """Context manager: coordinate accumulation order for k-NN calls made inside it (the grid
+    engine passes each dataset's columns sorted by descending variance)."""
+
+    def __init__(self, order):
+        self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+
+    def __enter__(self):
+        self.prev = getattr(_COL_ORDER, "v", None)
+        _COL_ORDER.v = self.order
+
+    def __exit__(self, *a):
+        _COL_ORDER.v = self.prev
+
+
+def variance_order(X):
+    """Columns of a host matrix by descending variance (for ``column_order``)."""
+    return np.argsort(-np.var(np.asarray(X, dtype=np.float64), axis=0), kind="stable").astype(np.int32)
+
+
+def knn(A, Q, k, col_order=None):
     L = _ready()
     assert A.dtype == torch.float64 and Q.dtype == torch.float64 and A.is_contiguous() and Q.is_contiguous()
     out = torch.empty((Q.shape[0], k), dtype=torch.int32, device=A.device)
-    check(L.f16_knn(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], k, _ptr(out), _stream()))
+    if col_order is None:
+        col_order = getattr(_COL_ORDER, "v", None)
+    co = None
+    if col_order is not None:
+        co = np.ascontiguousarray(col_order, dtype=np.int32)
+        assert co.shape[0] == A.shape[1]
+    check(L.f16_knn(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], k,
+                    ctypes.c_void_p(co.ctypes.data) if co is not None else None, _ptr(out), _stream()))
     return out
 
 

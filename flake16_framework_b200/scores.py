@@ -58,12 +58,14 @@ class GridData:
         self.proj_names = [projects[first[o]] for o in order]
         self.proj_id = rank[inv].astype(np.int32)
         self.n_proj = len(uniq)
+        self.col_order = {}     # (ft, fs, pre) -> columns by descending variance (k-NN early exit)
         self.datasets = {}      # (ft, fs, pre) -> float64 C-contiguous [N, d]
         self.labels = {}        # ft -> bool[N]
         self.folds = {}         # ft -> test_folds int[N]
         for (ft, fs, pre) in sorted({c[:3] for c in configs}):
             X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[ft], hp.FEATURE_SETS[fs])
             self.datasets[(ft, fs, pre)] = np.ascontiguousarray(hp.preprocess(X, pre))
+            self.col_order[(ft, fs, pre)] = ops.variance_order(self.datasets[(ft, fs, pre)])
             if ft not in self.labels:
                 self.labels[ft] = y
                 self.folds[ft] = hp.stratified_kfold_test_folds(y, n_splits, True, 0)
@@ -150,6 +152,7 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
 
     cache = {}
     keep = []      # tensors read by side streams stay referenced until the unit is done
+    n_fits = [0]
 
     def nn4(tag, X):
         if tag not in cache:
@@ -206,7 +209,8 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
             if model not in models:
                 continue
             ci = cfg_index[ds_key + (bal, model)]
-            side = model_streams[model]
+            lanes = model_streams[model]
+            side = lanes[BALANCINGS.index(bal) % len(lanes)]
             side.wait_event(ready)
             with torch.cuda.stream(side):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -218,8 +222,9 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
                 ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
                 keep.append(pred)
             timers.append((ci, e0, e1, e2, forest))
-    for side in model_streams.values():
-        side.synchronize()
+    for lanes in model_streams.values():
+        for side in lanes:
+            side.synchronize()
     return n_tr
 
 
@@ -265,7 +270,9 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
     def worker():
         torch.cuda.set_device(device)
         stream = torch.cuda.Stream(device=device)
-        model_streams = {m: torch.cuda.Stream(device=device) for m in MODELS}
+        # several forests of one unit in flight: 3 side streams per forest model, 2 for the tree
+        model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else 3)]
+                         for m in MODELS}
         timers = []
         try:
             with torch.cuda.stream(stream):
@@ -274,7 +281,9 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
                         u = q.get_nowait()
                     except queue.Empty:
                         break
-                    _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers, model_streams)
+                    with ops.column_order(gd.col_order[u[0]]):
+                        _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers,
+                                  model_streams)
                     stream.synchronize()
                     for ci, e0, e1, e2, forest in timers:
                         forest.status()

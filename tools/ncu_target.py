@@ -20,6 +20,6 @@ for kind in (ops.KIND_ET, ops.KIND_RF, ops.KIND_DT):
     p = f.predict(Xte)
     f.status(); f.free()
 Xtr64 = ops.gather_rows_f64(Xd, tri)
-nn = ops.knn(Xtr64, Xtr64, 4)
+nn = ops.knn(Xtr64, Xtr64, 4, ops.variance_order(X))
 torch.cuda.synchronize()
 print("ncu target done", int(p.sum()), int(nn.sum()))

@@ -24,7 +24,8 @@ def timeit(name, fn, reps=1):
     return r
 
 if what in ("all", "ops"):
-    for fs, pre in (("Flake16", "None"), ("Flake16", "Scaling"), ("FlakeFlagger", "None")):
+    for fs, pre in ((("Flake16", "Scaling"), ("FlakeFlagger", "None")) if os.environ.get("F16_LIB") else
+                    (("Flake16", "None"), ("Flake16", "Scaling"), ("FlakeFlagger", "None"))):
         X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES["NOD"], hp.FEATURE_SETS[fs])
         X = np.ascontiguousarray(hp.preprocess(X, pre)); d = X.shape[1]
         tf = hp.stratified_kfold_test_folds(y)
@@ -41,10 +42,10 @@ if what in ("all", "ops"):
             timeit("predict %s" % name, lambda: f.predict(Xte))
             f.free()
         Xtr64 = ops.gather_rows_f64(Xd, tri)
-        timeit("knn k=4 n=%d" % len(tr), lambda: ops.knn(Xtr64, Xtr64, 4))
+        timeit("knn k=4 n=%d" % len(tr), lambda: ops.knn(Xtr64, Xtr64, 4, ops.variance_order(X)))
         c1 = int(y[tr].sum())
         Xs, ys = timeit("smote", lambda: ops.smote(Xtr64, ytr, c1, len(tr) - c1, 1, 0, 5))
-        timeit("knn k=4 n=%d (after SMOTE)" % Xs.shape[0], lambda: ops.knn(Xs, Xs, 4))
+        timeit("knn k=4 n=%d (after SMOTE)" % Xs.shape[0], lambda: ops.knn(Xs, Xs, 4, ops.variance_order(X)))
         Xrs = ops.rows_f32(Xs.contiguous()); sidx2 = ops.argsort_columns(Xrs, d)
         for kind, name in ((ops.KIND_ET, "ET"), (ops.KIND_RF, "RF"), (ops.KIND_DT, "DT")):
             f = timeit("fit %s after SMOTE n=%d" % (name, Xs.shape[0]), lambda: ops.forest_fit(Xrs, ys.contiguous(), d, kind, 100, 0, sidx2))
@@ -54,7 +55,7 @@ if what in ("all", "ops"):
 if what in ("all", "grid"):
     L.f16_set_profiling(0)
     cfgs = [c for c in S.all_config_keys() if c[0] == "NOD" and c[1] == "Flake16" and c[2] == "Scaling"]
-    for ns in (1, 4, 8):
+    for ns in ((8, 16) if os.environ.get("F16_LIB") else (1, 4, 8, 16)):
         torch.cuda.synchronize(); t = time.time()
         S.run_grid(parsed, cfgs, n_streams=ns)
         torch.cuda.synchronize(); dt = time.time() - t
