@@ -159,6 +159,7 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     }
     size_t dyn = 0;
     if (best) {
+        CUDA_TRY(cudaMallocAsync((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
         P.side_words = (int)((n + 31) / 32);
         if (P.side_words > F16_SIDE_SMEM_MAX_WORDS) {
             CUDA_TRY(cudaMallocAsync((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words, st));
@@ -181,6 +182,7 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     CUDA_TRY(cudaFreeAsync(rr_dev, st));
     if (bw) CUDA_TRY(cudaFreeAsync(bw, st));
     if (P.side_global) CUDA_TRY(cudaFreeAsync(P.side_global, st));
+    if (P.lid) CUDA_TRY(cudaFreeAsync(P.lid, st));
     *out = F;
     return F16_OK;
 }

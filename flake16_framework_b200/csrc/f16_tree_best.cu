@@ -105,33 +105,66 @@ __device__ __forceinline__ void warp_partition(const uint32_t* src, uint32_t* ds
     const int lane = threadIdx.x & 31;
     int run_l = 0;
     constexpr int WPU = 8;
-    for (int base = 0; base < n; base += 32 * WPU) {
-        uint32_t e[WPU]; bool valid[WPU], left[WPU];
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0;
+    // full rounds: 8 x 32 entries, every load issued before the first use
+    for (; base + 32 * WPU <= n; base += 32 * WPU) {
+        uint32_t e[WPU]; bool left[WPU];
 #pragma unroll
-        for (int j = 0; j < WPU; j++) {
-            int p = base + j * 32 + lane;
-            valid[j] = p < n;
-            e[j] = valid[j] ? src[start + p] : 0u;
-        }
+        for (int j = 0; j < WPU; j++) e[j] = src[start + base + j * 32 + lane];
 #pragma unroll
-        for (int j = 0; j < WPU; j++) left[j] = valid[j] && side_get(side, f16_id(e[j]));
+        for (int j = 0; j < WPU; j++) left[j] = side_get(side, f16_id(e[j]));
 #pragma unroll
         for (int j = 0; j < WPU; j++) {
             unsigned bal = __ballot_sync(F16_FULL, left[j]);
-            int lrank = __popc(bal & ((1u << lane) - 1u));
-            int pb = base + j * 32;
-            if (valid[j]) {
-                if (left[j]) dst[start + run_l + lrank] = e[j];
-                else dst[start + n_left + (pb - run_l) + (lane - lrank)] = e[j];
-            }
+            int lrank = __popc(bal & lt);
+            int pos = left[j] ? (run_l + lrank) : (n_left + (base + j * 32 - run_l) + (lane - lrank));
+            dst[start + pos] = e[j];
             run_l += __popc(bal);
+        }
+    }
+    // tail: up to 4 tiles per round, only the tiles that exist are executed (small nodes pay
+    // for what they have)
+    for (; base < n; base += 128) {
+        const int nj = min(4, (n - base + 31) >> 5);
+        uint32_t e[4]; bool valid[4], left[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < nj) { int p = base + j * 32 + lane; valid[j] = p < n; e[j] = valid[j] ? src[start + p] : 0u; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < nj) left[j] = valid[j] && side_get(side, f16_id(e[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < nj) {
+                unsigned bal = __ballot_sync(F16_FULL, left[j]);
+                int lrank = __popc(bal & lt);
+                if (valid[j])
+                    dst[start + (left[j] ? (run_l + lrank) : (n_left + (base + j * 32 - run_l) + (lane - lrank)))] = e[j];
+                run_l += __popc(bal);
+            }
         }
     }
 }
 
+// SHARED regime: a node with at most SB rows is relocated once into shared memory - its d sorted
+// lists (entries re-indexed to local row ids), its feature values (column-major, odd stride) - and
+// its whole subtree is grown by the same block-wide code on those arrays: no global loads, only
+// node records go to HBM.  The region aliases the side bits of the GLOBAL regime (never live at
+// the same time: every node marks all of its rows before its partitions read them).
+template <int DP> struct BestSub { static constexpr int SB = (DP == 16) ? 256 : 512; };
+#define F16_BEST_SUB_BYTES(DP) (2 * (DP) * BestSub<DP>::SB * 4 + (DP) * (BestSub<DP>::SB + 1) * 4 + BestSub<DP>::SB / 8)
+
 template <int DP>
 __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
+    constexpr int SB = BestSub<DP>::SB;
+    constexpr int SBP = SB + 1;
     extern __shared__ uint32_t s_side_dyn[];
+    uint32_t* s_ord = s_side_dyn;                                           // [2][DP][SB]
+    float* s_val = reinterpret_cast<float*>(s_side_dyn + 2 * DP * SB);      // [DP][SBP]
+    uint32_t* s_side_l = s_side_dyn + 2 * DP * SB + DP * SBP;               // [SB / 32]
     __shared__ Ctl c;
     __shared__ DrawState ds;
     __shared__ F16StackRec s_stack[SSTK];
@@ -211,17 +244,57 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
         if (tid == 0) pop_node(c, stk);
         __syncthreads();
         if (c.done) break;
-        const int start = c.start, nn = c.end - c.start;
-        const uint32_t* src = (c.depth & 1) ? ord1 : ord0;
-        uint32_t* dst = (c.depth & 1) ? ord0 : ord1;
+        const int nn = c.end - c.start;
+        if (!c.leaf && !c.in_smem && nn <= SB && (~c.const_mask & ((1u << d) - 1u))) {
+            // ================= relocate the node into shared memory
+            const uint32_t* gsrc = (c.depth & 1) ? ord1 : ord0;
+            uint32_t* lid = P.lid + (size_t)t * n;
+            const int f0 = __ffs(~c.const_mask & ((1u << d) - 1u)) - 1;   // a list that is maintained
+            const int gstart = c.start;
+            {
+                constexpr int Q = DP / 4;
+                const int q = tid % Q;
+                const uint32_t* o = gsrc + (size_t)f0 * n + gstart;
+                for (int p = tid / Q; p < nn; p += NT / Q) {
+                    uint32_t gid = f16_id(o[p]);
+                    float4 v = __ldg(reinterpret_cast<const float4*>(X + (size_t)gid * DP) + q);
+                    s_val[(q * 4 + 0) * SBP + p] = v.x;
+                    s_val[(q * 4 + 1) * SBP + p] = v.y;
+                    s_val[(q * 4 + 2) * SBP + p] = v.z;
+                    s_val[(q * 4 + 3) * SBP + p] = v.w;
+                    if (q == 0) lid[gid] = (uint32_t)p;
+                }
+            }
+            __syncthreads();
+            uint32_t* sdst = s_ord + ((c.depth & 1) ? DP * SB : 0);
+            for (int f = warp; f < d; f += NW) {
+                if ((c.const_mask >> f) & 1u) continue;
+                const uint32_t* o = gsrc + (size_t)f * n + gstart;
+                for (int p = lane; p < nn; p += 32) {
+                    uint32_t e = o[p];
+                    sdst[f * SB + p] = (e & ~F16_ID_MASK) | lid[f16_id(e)];
+                }
+            }
+            if (tid == 0) { c.in_smem = 1; c.start = 0; c.end = nn; }
+            __syncthreads();
+        }
+        const bool sm = c.in_smem != 0;
+        const int start = c.start;
+        const int stride = sm ? SB : n;
+        const uint32_t* src = sm ? (s_ord + ((c.depth & 1) ? DP * SB : 0)) : ((c.depth & 1) ? ord1 : ord0);
+        uint32_t* dst = sm ? (s_ord + ((c.depth & 1) ? 0 : DP * SB)) : ((c.depth & 1) ? ord0 : ord1);
+        uint32_t* nside = sm ? s_side_l : side;
+        auto value = [&](uint32_t e, int f) -> float {
+            return sm ? s_val[f * SBP + f16_id(e)] : __ldg(X + (size_t)f16_id(e) * DP + f);
+        };
         int n_eval = 0;
 
         if (!c.leaf) {
             // ---- min / max of every not-yet-constant feature: ends of its sorted slice
             if (tid < d && !((c.const_mask >> tid) & 1u)) {
-                const uint32_t* o = src + (size_t)tid * n;
-                s_min[tid] = __ldg(X + (size_t)f16_id(o[start]) * DP + tid);
-                s_max[tid] = __ldg(X + (size_t)f16_id(o[start + nn - 1]) * DP + tid);
+                const uint32_t* o = src + (size_t)tid * stride;
+                s_min[tid] = value(o[start], tid);
+                s_max[tid] = value(o[start + nn - 1], tid);
             }
             __syncthreads();
             // ---- Fisher-Yates feature draw (thread 0)
@@ -262,7 +335,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             const int t0 = c.c0, t1 = c.c1;
             for (int k = warp; k < n_eval; k += NW) {
                 const int f = s_eval_f[k];
-                const uint32_t* o = src + (size_t)f * n + start;
+                const uint32_t* o = src + (size_t)f * stride + start;
                 unsigned long long carry = 0;
                 float prev_last = 0.f;
                 // 4 consecutive entries per lane: all 8 loads of a round are in flight together,
@@ -274,7 +347,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     for (int j = 0; j < 4; j++) e[j] = (p0 + j < nn) ? o[p0 + j] : 0u;
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        v[j] = (p0 + j < nn) ? __ldg(X + (size_t)f16_id(e[j]) * DP + f) : INFINITY;
+                        v[j] = (p0 + j < nn) ? value(e[j], f) : INFINITY;
                     unsigned long long run = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -337,18 +410,18 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             // ---- mark the side of every row of the node (the winning feature's slice is
             //      sorted, so the left rows are its first n_left entries)
             const int n_left = c.n_left;
-            const uint32_t* o = src + (size_t)c.best_f * n + start;
+            const uint32_t* o = src + (size_t)c.best_f * stride + start;
             for (int p = tid; p < nn; p += NT) {
                 uint32_t id = f16_id(o[p]);
-                if (p < n_left) atomicOr(&side[id >> 5], 1u << (id & 31));
-                else atomicAnd(&side[id >> 5], ~(1u << (id & 31)));
+                if (p < n_left) atomicOr(&nside[id >> 5], 1u << (id & 31));
+                else atomicAnd(&nside[id >> 5], ~(1u << (id & 31)));
             }
             __syncthreads();
             // ---- stable partition of every still-useful feature array, a warp per array
             const uint32_t keep_mask = ~c.const_mask_out;
             for (int f = warp; f < d; f += NW) {
                 if (!((keep_mask >> f) & 1u)) continue;
-                warp_partition(src + (size_t)f * n, dst + (size_t)f * n, start, nn, n_left, side);
+                warp_partition(src + (size_t)f * stride, dst + (size_t)f * stride, start, nn, n_left, nside);
             }
             __syncthreads();
         }
@@ -358,12 +431,17 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
 
 int F16_CAT(f16_launch_build_best, F16_VARIANT)(const F16FitParams& P, size_t dyn_smem, cudaStream_t st) {
     cudaError_t e;
+    const size_t max_dyn = 4 * F16_SIDE_SMEM_MAX_WORDS;     // 64 KiB >= both regimes' needs
     if (P.dp == 8) {
-        e = cudaFuncSetAttribute(k_build_best<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * F16_SIDE_SMEM_MAX_WORDS);
+        size_t need = F16_BEST_SUB_BYTES(8);
+        if (dyn_smem < need) dyn_smem = need;
+        e = cudaFuncSetAttribute(k_build_best<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn);
         if (e != cudaSuccess) return F16_ERR_CUDA;
         k_build_best<8><<<P.n_trees, NT, dyn_smem, st>>>(P);
     } else {
-        e = cudaFuncSetAttribute(k_build_best<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * F16_SIDE_SMEM_MAX_WORDS);
+        size_t need = F16_BEST_SUB_BYTES(16);
+        if (dyn_smem < need) dyn_smem = need;
+        e = cudaFuncSetAttribute(k_build_best<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn);
         if (e != cudaSuccess) return F16_ERR_CUDA;
         k_build_best<16><<<P.n_trees, NT, dyn_smem, st>>>(P);
     }

@@ -135,31 +135,40 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
     int run_l = 0, buf = 0;
     for (int base = 0; base < n; base += NT * PU, buf ^= 1) {
         uint32_t e[PU]; bool valid[PU], left[PU]; unsigned bal[PU];
+        const int nj = min(PU, (n - base + NT - 1) / NT);     // sub-tiles that exist (uniform)
 #pragma unroll
         for (int j = 0; j < PU; j++) {
-            int p = base + j * NT + tid;
-            valid[j] = p < n;
-            e[j] = valid[j] ? src[start + p] : 0u;
+            if (j < nj) {
+                int p = base + j * NT + tid;
+                valid[j] = p < n;
+                e[j] = valid[j] ? src[start + p] : 0u;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < PU; j++) left[j] = valid[j] && pred(e[j]);
+        for (int j = 0; j < PU; j++) {
+            if (j < nj) left[j] = valid[j] && pred(e[j]);
+        }
 #pragma unroll
         for (int j = 0; j < PU; j++) {
-            bal[j] = __ballot_sync(F16_FULL, left[j]);
-            if (lane == 0) s_wcnt[buf][j][warp] = __popc(bal[j]);
+            if (j < nj) {
+                bal[j] = __ballot_sync(F16_FULL, left[j]);
+                if (lane == 0) s_wcnt[buf][j][warp] = __popc(bal[j]);
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < PU; j++) {
-            int before = 0, tot = 0;
+            if (j < nj) {
+                int before = 0, tot = 0;
 #pragma unroll
-            for (int q = 0; q < NW; q++) { int cq = s_wcnt[buf][j][q]; if (q < warp) before += cq; tot += cq; }
-            int lrank = before + __popc(bal[j] & ((1u << lane) - 1u));
-            if (valid[j]) {
-                if (left[j]) dst[start + run_l + lrank] = e[j];
-                else dst[start + n_left + (base + j * NT - run_l) + (tid - lrank)] = e[j];
+                for (int q = 0; q < NW; q++) { int cq = s_wcnt[buf][j][q]; if (q < warp) before += cq; tot += cq; }
+                int lrank = before + __popc(bal[j] & ((1u << lane) - 1u));
+                if (valid[j]) {
+                    if (left[j]) dst[start + run_l + lrank] = e[j];
+                    else dst[start + n_left + (base + j * NT - run_l) + (tid - lrank)] = e[j];
+                }
+                run_l += tot;
             }
-            run_l += tot;
         }
     }
 }
