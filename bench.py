@@ -95,14 +95,19 @@ def cpu_sample(tests_file, steps_total):
     base = [("NOD", "Flake16", "None", "None", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
     smote = [("NOD", "Flake16", "None", "SMOTE", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
     if steps_total <= 2:
-        tasks = base + smote
+        kinds = base + smote
     elif steps_total <= 6:
-        tasks = base
+        kinds = base
     else:
-        tasks = base[:2]
-    desc = ("fold 1 of 10 of %d configs (%s) on the same tests.json, one process per task"
-            % (len(tasks), "; ".join("/".join(t[2:]) for t in tasks)))
-    return tasks, desc, min(cores, len(tasks))
+        kinds = base[:2]
+    # fill the host: the same bounded task set replicated so that every core has one
+    # single-threaded call chain, exactly how the reference's Pool(N_PROC) loads the machine
+    workers = max(1, min(cores, 96))
+    reps = max(1, workers // len(kinds))
+    tasks = kinds * reps
+    desc = ("fold 1 of 10 of %d config kinds (%s) x %d replicas = %d single-fold tasks on the same tests.json, "
+            "one single-threaded process per task" % (len(kinds), "; ".join("/".join(t[2:]) for t in kinds), reps, len(tasks)))
+    return tasks, desc, min(workers, len(tasks))
 
 
 def run_cpu_sample(tests_file, tasks, workers):

@@ -6,13 +6,21 @@
 // brute force (ArgKmin) for d > 15 and a KD-tree for d <= 15 (sklearn/neighbors/_base.py:615-648);
 // both are exact searches, so one exact kernel serves both feature sets.
 //
-// Distances are direct sums of squared differences accumulated in float64 (no
-// |x|^2 - 2xy + |y|^2 expansion: raw Flake16 columns reach 1e8 and the expansion cancels
+// The distance that DECIDES is the direct sum of squared differences accumulated in float64
+// (no |x|^2 - 2xy + |y|^2 expansion: raw Flake16 columns reach 1e8 and the expansion cancels
 // catastrophically).  Tie rule: smaller distance first, then lower reference index.
 //
-// This is an N^2*d FP64 CUDA-core problem (no tensor-core path for float64 on sm_100a that
-// keeps exactness); the reference rows are staged through shared memory and every thread
-// keeps its query and its running top-k in registers.
+// This is an N^2*d FP64 CUDA-core problem (roofline: the FP64 pipe, not HBM).  To halve the
+// FP64 instructions per pair, every pair first goes through a CONSERVATIVE FILTER in the
+// expanded form: acc = x.y - (1-eps)/2 (|x|^2 + |y|^2), one DFMA per coordinate; a pair can
+// only enter the top-k if acc > -bd_k/2, where eps bounds the rounding error of the expanded
+// form (|error| <= 2(d+6) u (|x|^2+|y|^2), u = 2^-53; eps = 2e-14 >= 180 u).  The few pairs
+// that pass are recomputed with the exact direct form, so the result is identical to the
+// unfiltered search.  The filter is evaluated on the first half of the coordinates first
+// (columns ordered by descending variance by the caller): a partial distance already beyond
+// the current k-th best for every lane of the warp skips the second half.
+// Reference rows are staged through shared memory together with their pre-scaled squared
+// norms; every thread keeps its query and its running top-k in registers.
 #include "f16_common.cuh"
 #include <math.h>
 #include <stdio.h>
@@ -30,55 +38,117 @@ extern "C" void f16_set_error(const char* fmt, ...);
 #define KT 128      // queries (threads) per block
 #define KTILE 64    // reference rows per shared-memory tile
 #define KMAX 8
+#define KNN_SCALE (-0.5 * (1.0 - 2.0e-14))
 
 struct KnnPerm { int c[F16_MAX_D]; };
 
-// Partial-distance early exit: the first H coordinates (the caller orders columns by
-// descending variance) are accumulated first; the remaining D-H are only evaluated when at
-// least one query of the warp could still beat its current k-th best distance.  The result
-// is exact: a skipped pair has a partial sum already >= the k-th best of every lane.
+// first-half coordinate count: even, so that halves fall on 16-byte (double2) boundaries
+template <int D> struct KnnCfg {
+    static constexpr int H = 2;    // prefix tested first: the two highest-variance coordinates
+    static constexpr int HH = (H < D) ? H : D;          // coordinates really in the first half
+    static constexpr int DPAD = (D + 1) & ~1;           // coordinates padded to a pair
+    static constexpr int TS = DPAD + 2;                 // tile row: {nh, nr, c0, c1, ..., pad}
+};
+
+// pre-scaled squared norms of every reference row: nrm[i] = {KNN_SCALE * |first H coords|^2,
+// KNN_SCALE * |remaining coords|^2} (coordinates in the permuted order)
+template <int D>
+__global__ void k_knn_norms(const double* __restrict__ A, int n, KnnPerm perm, double2* __restrict__ nrm) {
+    constexpr int HH = KnnCfg<D>::HH;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double h = 0.0, r = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        double v = A[(size_t)i * D + perm.c[c]];
+        if (c < HH) h = fma(v, v, h); else r = fma(v, v, r);
+    }
+    nrm[i] = make_double2(KNN_SCALE * h, KNN_SCALE * r);
+}
+
+// Each thread owns KQ = 2 queries (registers), so every 16-byte shared-memory load of a
+// reference row feeds 4 DFMAs: the kernel stays bound by the FP64 pipe, not by LDS issue.
+#define KQ 2
 template <int D, int K>
 __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n, const double* __restrict__ Q, int nq,
-                                            int32_t* __restrict__ out, KnnPerm perm) {
-    constexpr int H = (D + 1) / 2;
-    __shared__ double tile[KTILE * D];
+                                            int32_t* __restrict__ out, KnnPerm perm, const double2* __restrict__ nrm) {
+    constexpr int HH = KnnCfg<D>::HH, H2 = KnnCfg<D>::H / 2, DPAD = KnnCfg<D>::DPAD, P2 = DPAD / 2, TS = KnnCfg<D>::TS;
+    __shared__ __align__(16) double tile[KTILE * TS];
     const int tid = threadIdx.x;
-    const int qi = blockIdx.x * KT + tid;
-    double q[D];
+    double q[KQ][DPAD], qh[KQ], qr[KQ], bd[KQ][K], thr[KQ];
+    int bi[KQ][K], qi[KQ];
 #pragma unroll
-    for (int c = 0; c < D; c++) q[c] = (qi < nq) ? Q[(size_t)qi * D + perm.c[c]] : 0.0;
-    double bd[K];
-    int bi[K];
+    for (int u = 0; u < KQ; u++) {
+        qi[u] = blockIdx.x * (KT * KQ) + u * KT + tid;
+        qh[u] = 0.0; qr[u] = 0.0;
 #pragma unroll
-    for (int m = 0; m < K; m++) { bd[m] = INFINITY; bi[m] = -1; }
+        for (int c = 0; c < DPAD; c++) {
+            q[u][c] = (c < D && qi[u] < nq) ? Q[(size_t)qi[u] * D + perm.c[c]] : 0.0;
+            if (c < HH) qh[u] = fma(q[u][c], q[u][c], qh[u]); else qr[u] = fma(q[u][c], q[u][c], qr[u]);
+        }
+        qh[u] *= KNN_SCALE; qr[u] *= KNN_SCALE;
+#pragma unroll
+        for (int m = 0; m < K; m++) { bd[u][m] = INFINITY; bi[u][m] = -1; }
+        thr[u] = -INFINITY;                   // -bd[K-1] / 2
+    }
 
     for (int base = 0; base < n; base += KTILE) {
         int cnt = min(KTILE, n - base);
-        for (int i = tid; i < cnt * D; i += KT) {
-            int j = i / D, c = i - j * D;
-            tile[i] = A[(size_t)(base + j) * D + perm.c[c]];
+        for (int i = tid; i < cnt * DPAD; i += KT) {
+            int j = i / DPAD, c = i - j * DPAD;
+            tile[j * TS + 2 + c] = (c < D) ? A[(size_t)(base + j) * D + perm.c[c]] : 0.0;
+        }
+        for (int j = tid; j < cnt; j += KT) {
+            double2 v = nrm[base + j];
+            tile[j * TS] = v.x; tile[j * TS + 1] = v.y;
         }
         __syncthreads();
         for (int j = 0; j < cnt; j++) {
-            double s = 0.0;
+            const double2* t2 = reinterpret_cast<const double2*>(tile + j * TS);
+            const double2 nn = t2[0];
+            double acc[KQ];
+            const double2 v0 = t2[1];
+            bool go = false;
 #pragma unroll
-            for (int c = 0; c < H; c++) {
-                double df = q[c] - tile[j * D + c];
-                s = fma(df, df, s);
+            for (int u = 0; u < KQ; u++) {
+                acc[u] = fma(q[u][1], v0.y, fma(q[u][0], v0.x, qh[u] + nn.x));
+                go = go || (acc[u] > thr[u]);
             }
-            if (__any_sync(0xffffffffu, s < bd[K - 1])) {
+            if (__any_sync(0xffffffffu, go)) {
+                // remaining coordinates: two independent accumulators per query (the filter's
+                // error bound does not depend on the summation order)
+                double acb[KQ];
 #pragma unroll
-                for (int c = H; c < D; c++) {
-                    double df = q[c] - tile[j * D + c];
-                    s = fma(df, df, s);
+                for (int u = 0; u < KQ; u++) { acc[u] += qr[u] + nn.y; acb[u] = 0.0; }
+#pragma unroll
+                for (int p = H2; p < P2; p++) {
+                    const double2 v = t2[1 + p];
+#pragma unroll
+                    for (int u = 0; u < KQ; u++) { acc[u] = fma(q[u][2 * p], v.x, acc[u]); acb[u] = fma(q[u][2 * p + 1], v.y, acb[u]); }
                 }
-                if (s < bd[K - 1]) {
-                    bd[K - 1] = s; bi[K - 1] = base + j;
 #pragma unroll
-                    for (int m = K - 1; m > 0; m--) {
-                        if (bd[m] < bd[m - 1]) {
-                            double td = bd[m]; bd[m] = bd[m - 1]; bd[m - 1] = td;
-                            int ti = bi[m]; bi[m] = bi[m - 1]; bi[m - 1] = ti;
+                for (int u = 0; u < KQ; u++) acc[u] += acb[u];
+#pragma unroll
+                for (int u = 0; u < KQ; u++) {
+                    if (acc[u] > thr[u]) {
+                        // survivor of the conservative filter: the exact direct distance decides
+                        const double* t = tile + j * TS + 2;
+                        double s = 0.0;
+#pragma unroll
+                        for (int c = 0; c < D; c++) {
+                            double df = q[u][c] - t[c];
+                            s = fma(df, df, s);
+                        }
+                        if (s < bd[u][K - 1]) {
+                            bd[u][K - 1] = s; bi[u][K - 1] = base + j;
+#pragma unroll
+                            for (int m = K - 1; m > 0; m--) {
+                                if (bd[u][m] < bd[u][m - 1]) {
+                                    double td = bd[u][m]; bd[u][m] = bd[u][m - 1]; bd[u][m - 1] = td;
+                                    int ti = bi[u][m]; bi[u][m] = bi[u][m - 1]; bi[u][m - 1] = ti;
+                                }
+                            }
+                            thr[u] = -0.5 * bd[u][K - 1];
                         }
                     }
                 }
@@ -86,27 +156,32 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
         }
         __syncthreads();
     }
-    if (qi < nq) {
 #pragma unroll
-        for (int m = 0; m < K; m++) out[(size_t)qi * K + m] = bi[m];
+    for (int u = 0; u < KQ; u++) {
+        if (qi[u] < nq) {
+#pragma unroll
+            for (int m = 0; m < K; m++) out[(size_t)qi[u] * K + m] = bi[u][m];
+        }
     }
 }
 
 template <int D>
-static int launch_k(const double* A, int n, const double* Q, int nq, int k, int32_t* out, const KnnPerm& pm, cudaStream_t st) {
-    int grid = (nq + KT - 1) / KT;
+static int launch_k(const double* A, int n, const double* Q, int nq, int k, int32_t* out, const KnnPerm& pm,
+                    double2* nrm, cudaStream_t st) {
+    k_knn_norms<D><<<(n + 255) / 256, 256, 0, st>>>(A, n, pm, nrm);
+    int grid = (nq + KT * KQ - 1) / (KT * KQ);
     switch (k) {
-        case 2: k_knn<D, 2><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 4: k_knn<D, 4><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 6: k_knn<D, 6><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 1: k_knn<D, 1><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 3: k_knn<D, 3><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 5: k_knn<D, 5><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 7: k_knn<D, 7><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
-        case 8: k_knn<D, 8><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm); break;
+        case 2: k_knn<D, 2><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 4: k_knn<D, 4><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 6: k_knn<D, 6><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 1: k_knn<D, 1><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 3: k_knn<D, 3><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 5: k_knn<D, 5><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 7: k_knn<D, 7><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        case 8: k_knn<D, 8><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
         default: return F16_ERR_INVALID;
     }
-    f16_count_launch(1);
+    f16_count_launch(2);
     return F16_OK;
 }
 
@@ -133,9 +208,11 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
             pm.c[c] = col_order[c];
         }
     }
+    double2* nrm = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&nrm, sizeof(double2) * (size_t)n, st));
     int rc;
     switch (d) {
-#define CASE_D(DD) case DD: rc = launch_k<DD>(A_dev, (int)n, Q_dev, (int)nq, k, idx_dev, pm, st); break;
+#define CASE_D(DD) case DD: rc = launch_k<DD>(A_dev, (int)n, Q_dev, (int)nq, k, idx_dev, pm, nrm, st); break;
         CASE_D(1) CASE_D(2) CASE_D(3) CASE_D(4) CASE_D(5) CASE_D(6) CASE_D(7) CASE_D(8)
         CASE_D(9) CASE_D(10) CASE_D(11) CASE_D(12) CASE_D(13) CASE_D(14) CASE_D(15) CASE_D(16)
 #undef CASE_D
@@ -143,5 +220,6 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
     }
     if (rc) { f16_set_error("f16_knn: unsupported (d=%d, k=%d)", d, k); return rc; }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(nrm, st));
     return F16_OK;
 }

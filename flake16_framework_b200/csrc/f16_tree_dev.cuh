@@ -19,7 +19,7 @@
 #define F16_CAT(a, b) F16_CAT_(a, b)
 #define NW (NT / 32)
 #define F16_EPS 2.220446049250313e-16
-#define SSTK 64     // stack records cached in shared memory (deeper ones spill to global)
+#define SSTK 40     // stack records cached in shared memory (deeper ones spill to global)
 
 // ------------------------------------------------------------------ shared control block
 struct Ctl {
@@ -175,6 +175,7 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
 int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);
+int f16_launch_build_random_w(const F16FitParams& P, cudaStream_t st);
 int f16_launch_build_best_rf(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_build_best_dt(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

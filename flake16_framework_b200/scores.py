@@ -20,6 +20,7 @@ Python-float expressions, so they are bit-identical given identical counts.
 """
 
 import itertools
+import os
 import pickle
 import queue
 import threading
@@ -271,7 +272,8 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
         torch.cuda.set_device(device)
         stream = torch.cuda.Stream(device=device)
         # several forests of one unit in flight: 3 side streams per forest model, 2 for the tree
-        model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else 3)]
+        n_lanes = int(os.environ.get("F16_LANES", "3"))
+        model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
                          for m in MODELS}
         timers = []
         try:

@@ -148,10 +148,14 @@ def all_config_keys(grid=None):
 
 
 def _worker(args):
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     config_keys, tests_file, n_splits, max_folds, n_estimators = args
     grid = make_config_grid(n_estimators)
-    return get_scores(config_keys, tests_file, grid, n_splits, max_folds)
+    try:        # one single-threaded call chain per worker, like the reference's Pool(N_PROC)
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            return get_scores(config_keys, tests_file, grid, n_splits, max_folds)
+    except ImportError:
+        return get_scores(config_keys, tests_file, grid, n_splits, max_folds)
 
 
 def run_configs(configs, tests_file, processes=None, n_splits=10, max_folds=None,
