@@ -108,7 +108,7 @@ SIGNATURES = {
     "f16_forest_node_counts": ([c_void_p, c_void_p, c_void_p], c_int),
     "f16_forest_export": ([c_void_p, c_int32, c_int64] + [c_void_p] * 8 + [c_void_p], c_int),
     "f16_forest_free": ([c_void_p, c_void_p], None),
-    "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p], c_int),
+    "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p], c_int),
     "f16_smote_generate": ([c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p], c_int),
     "f16_tomek_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),

@@ -36,7 +36,7 @@ extern "C" void f16_set_error(const char* fmt, ...);
     } while (0)
 
 #define KT 128      // queries (threads) per block
-#define KTILE 64    // reference rows per shared-memory tile
+#define KTILE 128   // reference rows per shared-memory tile (two tiles in flight)
 #define KMAX 8
 #define KNN_SCALE (-0.5 * (1.0 - 2.0e-14))
 
@@ -50,30 +50,43 @@ template <int D> struct KnnCfg {
     static constexpr int TS = DPAD + 2;                 // tile row: {nh, nr, c0, c1, ..., pad}
 };
 
-// pre-scaled squared norms of every reference row: nrm[i] = {KNN_SCALE * |first H coords|^2,
-// KNN_SCALE * |remaining coords|^2} (coordinates in the permuted order)
+// Reference rows in tile layout, written once: Ap[i] = {KNN_SCALE * |first H coords|^2,
+// KNN_SCALE * |remaining coords|^2, c0, c1, ..., (pad)} with the coordinates in the permuted
+// order, so the search kernel stages tiles with plain 16-byte asynchronous copies.
 template <int D>
-__global__ void k_knn_norms(const double* __restrict__ A, int n, KnnPerm perm, double2* __restrict__ nrm) {
-    constexpr int HH = KnnCfg<D>::HH;
+__global__ void k_knn_prep(const double* __restrict__ A, int n, KnnPerm perm, double* __restrict__ Ap) {
+    constexpr int HH = KnnCfg<D>::HH, DPAD = KnnCfg<D>::DPAD, TS = KnnCfg<D>::TS;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double h = 0.0, r = 0.0;
+    double* o = Ap + (size_t)i * TS;
 #pragma unroll
-    for (int c = 0; c < D; c++) {
-        double v = A[(size_t)i * D + perm.c[c]];
+    for (int c = 0; c < DPAD; c++) {
+        double v = (c < D) ? A[(size_t)i * D + perm.c[c]] : 0.0;
         if (c < HH) h = fma(v, v, h); else r = fma(v, v, r);
+        o[2 + c] = v;
     }
-    nrm[i] = make_double2(KNN_SCALE * h, KNN_SCALE * r);
+    o[0] = KNN_SCALE * h; o[1] = KNN_SCALE * r;
 }
+
+__device__ __forceinline__ void knn_cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void knn_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void knn_cp_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
 // Each thread owns KQ = 2 queries (registers), so every 16-byte shared-memory load of a
 // reference row feeds 4 DFMAs: the kernel stays bound by the FP64 pipe, not by LDS issue.
 #define KQ 2
-template <int D, int K>
+// PREFIX: test the two leading (highest-variance) coordinates first and skip the rest of the
+// row when no lane of the warp can improve - pays off when those columns dominate the distance
+// (raw, unscaled features); without it the row is one uninterrupted DFMA stream.
+template <int D, int K, bool PREFIX>
 __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n, const double* __restrict__ Q, int nq,
-                                            int32_t* __restrict__ out, KnnPerm perm, const double2* __restrict__ nrm) {
+                                            int32_t* __restrict__ out, KnnPerm perm, const double* __restrict__ Ap) {
     constexpr int HH = KnnCfg<D>::HH, H2 = KnnCfg<D>::H / 2, DPAD = KnnCfg<D>::DPAD, P2 = DPAD / 2, TS = KnnCfg<D>::TS;
-    __shared__ __align__(16) double tile[KTILE * TS];
+    __shared__ __align__(16) double tiles[2][KTILE * TS];      // double buffered (cp.async)
     const int tid = threadIdx.x;
     double q[KQ][DPAD], qh[KQ], qr[KQ], bd[KQ][K], thr[KQ];
     int bi[KQ][K], qi[KQ];
@@ -92,17 +105,24 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
         thr[u] = -INFINITY;                   // -bd[K-1] / 2
     }
 
-    for (int base = 0; base < n; base += KTILE) {
-        int cnt = min(KTILE, n - base);
-        for (int i = tid; i < cnt * DPAD; i += KT) {
-            int j = i / DPAD, c = i - j * DPAD;
-            tile[j * TS + 2 + c] = (c < D) ? A[(size_t)(base + j) * D + perm.c[c]] : 0.0;
+    // stage tile 0
+    {
+        const int cnt = min(KTILE, n);
+        for (int i = tid; i < cnt * (TS / 2); i += KT) knn_cp_async16(&tiles[0][2 * i], Ap + 2 * (size_t)i);
+        knn_cp_commit();
+    }
+    int buf = 0;
+    for (int base = 0; base < n; base += KTILE, buf ^= 1) {
+        const int cnt = min(KTILE, n - base);
+        knn_cp_wait_all();
+        __syncthreads();                  // tile `buf` is complete; everyone is done with `buf ^ 1`
+        if (base + KTILE < n) {           // prefetch the next tile while this one is consumed
+            const int ncnt = min(KTILE, n - base - KTILE);
+            const double* g = Ap + (size_t)(base + KTILE) * TS;
+            for (int i = tid; i < ncnt * (TS / 2); i += KT) knn_cp_async16(&tiles[buf ^ 1][2 * i], g + 2 * (size_t)i);
+            knn_cp_commit();
         }
-        for (int j = tid; j < cnt; j += KT) {
-            double2 v = nrm[base + j];
-            tile[j * TS] = v.x; tile[j * TS + 1] = v.y;
-        }
-        __syncthreads();
+        const double* tile = tiles[buf];
         for (int j = 0; j < cnt; j++) {
             const double2* t2 = reinterpret_cast<const double2*>(tile + j * TS);
             const double2 nn = t2[0];
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
                 acc[u] = fma(q[u][1], v0.y, fma(q[u][0], v0.x, qh[u] + nn.x));
                 go = go || (acc[u] > thr[u]);
             }
-            if (__any_sync(0xffffffffu, go)) {
+            if (!PREFIX || __any_sync(0xffffffffu, go)) {
                 // remaining coordinates: two independent accumulators per query (the filter's
                 // error bound does not depend on the summation order)
                 double acb[KQ];
@@ -154,7 +174,6 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
                 }
             }
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int u = 0; u < KQ; u++) {
@@ -167,20 +186,19 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
 
 template <int D>
 static int launch_k(const double* A, int n, const double* Q, int nq, int k, int32_t* out, const KnnPerm& pm,
-                    double2* nrm, cudaStream_t st) {
-    k_knn_norms<D><<<(n + 255) / 256, 256, 0, st>>>(A, n, pm, nrm);
+                    double* nrm, bool prefix, cudaStream_t st) {
+    k_knn_prep<D><<<(n + 255) / 256, 256, 0, st>>>(A, n, pm, nrm);
     int grid = (nq + KT * KQ - 1) / (KT * KQ);
+#define KNN_LAUNCH(KK)                                                                          \
+    case KK:                                                                                    \
+        if (prefix) k_knn<D, KK, true><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm);          \
+        else k_knn<D, KK, false><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm);                \
+        break;
     switch (k) {
-        case 2: k_knn<D, 2><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 4: k_knn<D, 4><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 6: k_knn<D, 6><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 1: k_knn<D, 1><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 3: k_knn<D, 3><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 5: k_knn<D, 5><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 7: k_knn<D, 7><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
-        case 8: k_knn<D, 8><<<grid, KT, 0, st>>>(A, n, Q, nq, out, pm, nrm); break;
+        KNN_LAUNCH(1) KNN_LAUNCH(2) KNN_LAUNCH(3) KNN_LAUNCH(4) KNN_LAUNCH(5) KNN_LAUNCH(6) KNN_LAUNCH(7) KNN_LAUNCH(8)
         default: return F16_ERR_INVALID;
     }
+#undef KNN_LAUNCH
     f16_count_launch(2);
     return F16_OK;
 }
@@ -191,7 +209,7 @@ static int launch_k(const double* A, int n, const double* Q, int nq, int k, int3
 // col_order (host, d ints, or NULL): order in which the coordinates are accumulated; put the
 // highest-variance columns first to make the early exit effective.
 extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, int32_t k,
-                       const int32_t* col_order, int32_t* idx_dev, void* stream) {
+                       const int32_t* col_order, int32_t prefix_test, int32_t* idx_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!A_dev || !Q_dev || !idx_dev || n < 1 || nq < 0 || n > 0x7fffffff || nq > 0x7fffffff || d < 1 || d > F16_MAX_D) {
         f16_set_error("f16_knn: bad arguments"); return F16_ERR_INVALID;
@@ -208,11 +226,11 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
             pm.c[c] = col_order[c];
         }
     }
-    double2* nrm = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&nrm, sizeof(double2) * (size_t)n, st));
+    double* nrm = nullptr;      // reference rows in tile layout (norms + permuted coordinates)
+    CUDA_TRY(cudaMallocAsync((void**)&nrm, sizeof(double) * (size_t)n * (F16_MAX_D + 2), st));
     int rc;
     switch (d) {
-#define CASE_D(DD) case DD: rc = launch_k<DD>(A_dev, (int)n, Q_dev, (int)nq, k, idx_dev, pm, nrm, st); break;
+#define CASE_D(DD) case DD: rc = launch_k<DD>(A_dev, (int)n, Q_dev, (int)nq, k, idx_dev, pm, nrm, prefix_test != 0, st); break;
         CASE_D(1) CASE_D(2) CASE_D(3) CASE_D(4) CASE_D(5) CASE_D(6) CASE_D(7) CASE_D(8)
         CASE_D(9) CASE_D(10) CASE_D(11) CASE_D(12) CASE_D(13) CASE_D(14) CASE_D(15) CASE_D(16)
 #undef CASE_D

@@ -180,7 +180,12 @@ class column_order:
     engine passes each dataset's columns sorted by descending variance)."""
 
     def __init__(self, order):
-        self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        """``order``: None, a column permutation, or the (permutation, prefix_test) pair that
+        ``variance_order`` returns."""
+        prefix = 0
+        if isinstance(order, tuple):
+            order, prefix = order
+        self.order = None if order is None else (np.ascontiguousarray(order, dtype=np.int32), int(prefix))
 
     def __enter__(self):
         self.prev = getattr(_COL_ORDER, "v", None)
@@ -191,8 +196,13 @@ class column_order:
 
 
 def variance_order(X):
-    """Columns of a host matrix by descending variance (for ``column_order``)."""
-    return np.argsort(-np.var(np.asarray(X, dtype=np.float64), axis=0), kind="stable").astype(np.int32)
+    """(columns of a host matrix by descending variance, prefix_test flag): the early exit on
+    the two leading columns is enabled when they carry most of the total variance."""
+    var = np.var(np.asarray(X, dtype=np.float64), axis=0)
+    order = np.argsort(-var, kind="stable").astype(np.int32)
+    tot = float(var.sum())
+    prefix = int(tot > 0 and float(var[order[:2]].sum()) / tot > 0.8)
+    return order, prefix
 
 
 def knn(A, Q, k, col_order=None):
@@ -201,12 +211,14 @@ def knn(A, Q, k, col_order=None):
     out = torch.empty((Q.shape[0], k), dtype=torch.int32, device=A.device)
     if col_order is None:
         col_order = getattr(_COL_ORDER, "v", None)
-    co = None
+    co, prefix = None, 0
     if col_order is not None:
+        if isinstance(col_order, tuple):
+            col_order, prefix = col_order
         co = np.ascontiguousarray(col_order, dtype=np.int32)
         assert co.shape[0] == A.shape[1]
     check(L.f16_knn(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], k,
-                    ctypes.c_void_p(co.ctypes.data) if co is not None else None, _ptr(out), _stream()))
+                    ctypes.c_void_p(co.ctypes.data) if co is not None else None, int(prefix), _ptr(out), _stream()))
     return out
 
 
