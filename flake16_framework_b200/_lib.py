@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("F16_LIB") or os.path.join(_HERE, "libf16_b200.so")
 
 # Tree-kernel tunables (threads per tree CTA, min CTAs/SM, rows of the shared-memory regime).
 TUNE = {"ET_NT": 256, "ET_MINB": 4, "ET_S16": 512, "ET_S8": 1024,
-        "RF_NT": 256, "RF_MINB": 3, "DT_NT": 256, "DT_MINB": 1}
+        "RF_NT": 256, "RF_MINB": 3, "DT_NT": 512, "DT_MINB": 1}
 
 
 def _sources(tune):

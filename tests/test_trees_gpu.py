@@ -92,3 +92,46 @@ def test_full_100_trees_counts(cuda):
         our = _ours(kind, 100).fit(X[:5400], y[:5400])
         assert np.array_equal(ref.predict(X[5400:]), our.predict(X[5400:])), kind
         assert int(our.forest_.node_counts().sum()) == sum(e.tree_.node_count for e in ref.estimators_), kind
+
+
+@pytest.mark.parametrize("kind", ["ET", "RF", "DT"])
+def test_edge_cases(cuda, kind):
+    """Degenerate inputs the estimators must survive like scikit-learn does: one row, two rows,
+    a single class, all-constant features, empty prediction batch."""
+    rs = np.random.RandomState(11)
+    # one row / two rows
+    for n in (1, 2, 3):
+        X = rs.rand(n, 4)
+        y = np.arange(n) % 2 == 0
+        _check(kind, X, y, X, n_estimators=4)
+    # a single class: the root is a leaf
+    X = rs.rand(50, 6)
+    y = np.zeros(50, dtype=bool)
+    our = _ours(kind, 3).fit(X, y)
+    assert list(our.forest_.node_counts()) == [1] * (1 if kind == "DT" else 3)
+    assert not our.predict(X).any()
+    # all features constant: no valid split anywhere
+    Xc = np.ones((40, 5))
+    yc = rs.rand(40) < 0.5
+    _check(kind, Xc, yc, Xc, n_estimators=3)
+    # empty prediction batch
+    our = _ours(kind, 3).fit(X, rs.rand(50) < 0.5)
+    assert our.predict(np.zeros((0, 6))).shape == (0,)
+
+
+def test_bad_inputs_raise(cuda):
+    from flake16_framework_b200 import estimators as est
+    from flake16_framework_b200._lib import F16Error
+    X = np.random.RandomState(0).rand(30, 4)
+    y = np.arange(30) % 2 == 0
+    with pytest.raises(ValueError):
+        est.ExtraTreesClassifier(random_state=0).fit(X, y[:-1])
+    with pytest.raises(ValueError):
+        est.RandomForestClassifier(random_state=0).fit(X, np.arange(30) % 3)
+    m = est.DecisionTreeClassifier(random_state=0).fit(X, y)
+    with pytest.raises(ValueError):
+        m.predict(X[:, :3])
+    with pytest.raises((ValueError, F16Error)):
+        est.RandomForestClassifier(random_state=0).fit(np.zeros((10, 17)), np.arange(10) % 2 == 0)
+    with pytest.raises(ValueError):
+        est.SMOTE(random_state=0).fit_resample(X, np.arange(30) < 3)       # 3 minority rows < k + 1
