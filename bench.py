@@ -208,6 +208,7 @@ def ours_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     from flake16_framework_b200 import _lib, hostprep as hp, scores as S, synth
     L = _lib.lib()

@@ -37,6 +37,7 @@ def _sources(tune):
         ("f16_misc.cu", "", ["-fmad=false"]),
         ("f16_sort.cu", "", []),
         ("f16_knn.cu", "", []),
+        ("f16_knn32.cu", "", []),
     )
 
 

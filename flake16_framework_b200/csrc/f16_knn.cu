@@ -42,6 +42,9 @@ extern "C" void f16_set_error(const char* fmt, ...);
 
 struct KnnPerm { int c[F16_MAX_D]; };
 
+int f16_knn32_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
+                     float* c32, double* an, cudaStream_t st);
+
 // first-half coordinate count: even, so that halves fall on 16-byte (double2) boundaries
 template <int D> struct KnnCfg {
     static constexpr int H = 2;    // prefix tested first: the two highest-variance coordinates
@@ -225,6 +228,16 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
             seen |= 1u << col_order[c];
             pm.c[c] = col_order[c];
         }
+    }
+    if (prefix_test == 2) {     // float32 conservative filter (f16_knn32.cu); falls through if unsupported
+        float* c32 = nullptr; double* an = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&c32, sizeof(float) * (size_t)n * F16_MAX_D, st));
+        CUDA_TRY(cudaMallocAsync((void**)&an, sizeof(double) * (size_t)n, st));
+        int r32 = f16_knn32_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, c32, an, st);
+        CUDA_TRY(cudaFreeAsync(c32, st));
+        CUDA_TRY(cudaFreeAsync(an, st));
+        if (r32 == F16_OK) { CUDA_TRY(cudaGetLastError()); return F16_OK; }
+        prefix_test = 0;
     }
     double* nrm = nullptr;      // reference rows in tile layout (norms + permuted coordinates)
     CUDA_TRY(cudaMallocAsync((void**)&nrm, sizeof(double) * (size_t)n * (F16_MAX_D + 2), st));

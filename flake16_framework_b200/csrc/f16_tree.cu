@@ -161,7 +161,9 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     if (best) {
         CUDA_TRY(cudaMallocAsync((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
         P.side_words = (int)((n + 31) / 32);
-        if (P.side_words > F16_SIDE_SMEM_MAX_WORDS) {
+        // F16_FORCE_GLOBAL_SIDE=1 exercises the > 524288-row path on small inputs (tests)
+        static const int force_global_side = getenv("F16_FORCE_GLOBAL_SIDE") ? atoi(getenv("F16_FORCE_GLOBAL_SIDE")) : 0;
+        if (P.side_words > F16_SIDE_SMEM_MAX_WORDS || force_global_side) {
             CUDA_TRY(cudaMallocAsync((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words, st));
         } else {
             dyn = sizeof(uint32_t) * (size_t)P.side_words;

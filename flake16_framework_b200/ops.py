@@ -196,13 +196,21 @@ class column_order:
 
 
 def variance_order(X):
-    """(columns of a host matrix by descending variance, prefix_test flag): the early exit on
-    the two leading columns is enabled when they carry most of the total variance."""
-    var = np.var(np.asarray(X, dtype=np.float64), axis=0)
+    """(columns of a host matrix by descending variance, filter mode) for ``f16_knn``:
+    mode 1 - float64 filter with the early exit on the two leading columns, when they carry most
+             of the total variance (raw, unscaled features);
+    mode 2 - float32 filter, when every column is centred (|mean| <= 3 std: standardised or
+             PCA-rotated data), so that float32 rounding is negligible against neighbour distances;
+    mode 0 - plain float64 filter otherwise.  The modes only differ in speed, never in result."""
+    X = np.asarray(X, dtype=np.float64)
+    var = np.var(X, axis=0)
     order = np.argsort(-var, kind="stable").astype(np.int32)
     tot = float(var.sum())
-    prefix = int(tot > 0 and float(var[order[:2]].sum()) / tot > 0.8)
-    return order, prefix
+    if tot > 0 and float(var[order[:2]].sum()) / tot > 0.8:
+        return order, 1
+    if np.all(np.abs(X.mean(axis=0)) <= 3.0 * np.sqrt(var) + 1e-300):
+        return order, 2
+    return order, 0
 
 
 def knn(A, Q, k, col_order=None):

@@ -63,7 +63,7 @@ def test_knn_matches_sklearn(cuda, cfg):
         assert frac == 1.0, "k=%d: %.6f of rows have identical neighbour lists" % (k, frac)
         # column order / prefix early exit are pure scheduling: same result
         order, prefix = ops.variance_order(X)
-        for co in ((order, prefix), (order, 1), (order[::-1].copy(), 0)):
+        for co in ((order, prefix), (order, 1), (order, 2), (order[::-1].copy(), 0)):
             assert np.array_equal(ops.knn(Xd, Xd, k, co).cpu().numpy(), ours), (k, co[1])
 
 

@@ -135,3 +135,26 @@ def test_bad_inputs_raise(cuda):
         est.RandomForestClassifier(random_state=0).fit(np.zeros((10, 17)), np.arange(10) % 2 == 0)
     with pytest.raises(ValueError):
         est.SMOTE(random_state=0).fit_resample(X, np.arange(30) < 3)       # 3 minority rows < k + 1
+
+
+def test_global_side_bits_path(cuda):
+    """Training sets above 524 288 rows keep the best-splitter's side bits in global memory; force
+    that path on a small input (env switch read once per process -> subprocess) and check parity."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from util import make_dataset, compare_trees, tree_arrays_sklearn\n"
+        "from sklearn.ensemble import RandomForestClassifier as SK\n"
+        "from flake16_framework_b200.estimators import RandomForestClassifier as OURS\n"
+        "X, y, _ = make_dataset(3000)\n"
+        "ref = SK(random_state=0, n_estimators=4).fit(X, y); our = OURS(random_state=0, n_estimators=4).fit(X, y)\n"
+        "errs = []\n"
+        "for t, e in enumerate(ref.estimators_): errs += compare_trees(our.forest_.export_tree(t), tree_arrays_sklearn(e), str(t))\n"
+        "assert not errs, errs[:3]\n"
+        "print('GLOBAL_SIDE_OK')\n" % (root, os.path.join(root, "tests")))
+    out = subprocess.check_output([sys.executable, "-c", code], env=dict(os.environ, F16_FORCE_GLOBAL_SIDE="1"))
+    assert b"GLOBAL_SIDE_OK" in out
