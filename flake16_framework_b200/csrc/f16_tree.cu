@@ -13,6 +13,7 @@
 
 extern "C" void f16_set_error(const char* fmt, ...);
 extern "C" int f16_get_profiling(void);
+extern "C" cudaError_t f16_malloc_async(void** p, size_t bytes, cudaStream_t st);
 
 #define CUDA_TRY(x)                                                                     \
     do {                                                                                \
@@ -95,7 +96,7 @@ extern "C" int f16_bootstrap_counts(const uint32_t* tree_seed_host, int32_t n_tr
     if (n < 1 || n > F16_MAX_ROWS) { f16_set_error("f16_bootstrap_counts: n out of range"); return F16_ERR_INVALID; }
     size_t stride = align_up((size_t)n, 4);
     uint32_t* seeds_dev = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&seeds_dev, sizeof(uint32_t) * n_trees, st));
+    CUDA_TRY(f16_malloc_async((void**)&seeds_dev, sizeof(uint32_t) * n_trees, st));
     CUDA_TRY(cudaMemcpyAsync(seeds_dev, tree_seed_host, sizeof(uint32_t) * n_trees, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(w_dev, 0, stride * n_trees, st));
     if (f16_launch_bootstrap(seeds_dev, n_trees, (int)n, (uint32_t*)w_dev, (int)(stride / 4), st)) {
@@ -138,33 +139,33 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     P.stack_cap = F16_STACK_CAP; P.node_cap = F->node_cap;
 
     uint32_t* rr_dev = nullptr; uint8_t* bw = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&F->nodes, sizeof(F16Node) * (size_t)n_trees * F->node_cap, st));
-    CUDA_TRY(cudaMallocAsync((void**)&F->node_count, sizeof(int32_t) * n_trees, st));
-    CUDA_TRY(cudaMallocAsync((void**)&F->err, sizeof(int32_t), st));
+    CUDA_TRY(f16_malloc_async((void**)&F->nodes, sizeof(F16Node) * (size_t)n_trees * F->node_cap, st));
+    CUDA_TRY(f16_malloc_async((void**)&F->node_count, sizeof(int32_t) * n_trees, st));
+    CUDA_TRY(f16_malloc_async((void**)&F->err, sizeof(int32_t), st));
     CUDA_TRY(cudaMemsetAsync(F->err, 0, sizeof(int32_t), st));
     CUDA_TRY(cudaMemsetAsync(F->node_count, 0, sizeof(int32_t) * n_trees, st));
-    CUDA_TRY(cudaMallocAsync((void**)&rr_dev, sizeof(uint32_t) * n_trees, st));
+    CUDA_TRY(f16_malloc_async((void**)&rr_dev, sizeof(uint32_t) * n_trees, st));
     CUDA_TRY(cudaMemcpyAsync(rr_dev, rr.data(), sizeof(uint32_t) * n_trees, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMallocAsync((void**)&P.stack, sizeof(F16StackRec) * (size_t)n_trees * P.stack_cap, st));
+    CUDA_TRY(f16_malloc_async((void**)&P.stack, sizeof(F16StackRec) * (size_t)n_trees * P.stack_cap, st));
     size_t buf_words = (size_t)n_trees * 2 * (best ? (size_t)d : 1) * (size_t)n;
-    CUDA_TRY(cudaMallocAsync((void**)&P.buf, sizeof(uint32_t) * buf_words, st));
+    CUDA_TRY(f16_malloc_async((void**)&P.buf, sizeof(uint32_t) * buf_words, st));
     P.rand_r_state = rr_dev; P.nodes = F->nodes; P.node_count = F->node_count; P.err = F->err;
 
     if (kind == F16_KIND_RF) {
         size_t stride = align_up((size_t)n, 4);
-        CUDA_TRY(cudaMallocAsync((void**)&bw, stride * n_trees, st));
+        CUDA_TRY(f16_malloc_async((void**)&bw, stride * n_trees, st));
         rc = f16_bootstrap_counts(tree_seed.data(), n_trees, n, bw, stream);
         if (rc) return rc;
         P.boot_w = bw;
     }
     size_t dyn = 0;
     if (best) {
-        CUDA_TRY(cudaMallocAsync((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
+        CUDA_TRY(f16_malloc_async((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
         P.side_words = (int)((n + 31) / 32);
         // F16_FORCE_GLOBAL_SIDE=1 exercises the > 524288-row path on small inputs (tests)
         static const int force_global_side = getenv("F16_FORCE_GLOBAL_SIDE") ? atoi(getenv("F16_FORCE_GLOBAL_SIDE")) : 0;
         if (P.side_words > F16_SIDE_SMEM_MAX_WORDS || force_global_side) {
-            CUDA_TRY(cudaMallocAsync((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words, st));
+            CUDA_TRY(f16_malloc_async((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words, st));
         } else {
             dyn = sizeof(uint32_t) * (size_t)P.side_words;
         }
@@ -195,7 +196,7 @@ extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64
     if (!F || !X_dev || !pred_dev || n < 0) { f16_set_error("f16_forest_predict: bad arguments"); return F16_ERR_INVALID; }
     if (n == 0) return F16_OK;
     int2* leaf = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&leaf, sizeof(int2) * (size_t)F->n_trees * n, st));
+    CUDA_TRY(f16_malloc_async((void**)&leaf, sizeof(int2) * (size_t)F->n_trees * n, st));
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)F->n_trees);
     if (F->dp == 8) k_predict_walk<8><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);
     else k_predict_walk<16><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);

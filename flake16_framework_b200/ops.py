@@ -199,17 +199,18 @@ def variance_order(X):
     """(columns of a host matrix by descending variance, filter mode) for ``f16_knn``:
     mode 1 - float64 filter with the early exit on the two leading columns, when they carry most
              of the total variance (raw, unscaled features);
-    mode 2 - float32 filter, when every column is centred (|mean| <= 3 std: standardised or
-             PCA-rotated data), so that float32 rounding is negligible against neighbour distances;
-    mode 0 - plain float64 filter otherwise.  The modes only differ in speed, never in result."""
+    mode 0 - plain float64 filter otherwise.
+    (mode 2, a float32 filter for centred data, exists in the library and is covered by the parity
+    tests, but is never selected: measured no faster than mode 0 on B200 - a 3-register FFMA
+    issues at the same 2 cycles per warp as a DFMA - and slower on SMOTE'd data, whose dense
+    synthetic clusters defeat a 1e-6-relative filter.)
+    The modes only differ in speed, never in result."""
     X = np.asarray(X, dtype=np.float64)
     var = np.var(X, axis=0)
     order = np.argsort(-var, kind="stable").astype(np.int32)
     tot = float(var.sum())
     if tot > 0 and float(var[order[:2]].sum()) / tot > 0.8:
         return order, 1
-    if np.all(np.abs(X.mean(axis=0)) <= 3.0 * np.sqrt(var) + 1e-300):
-        return order, 2
     return order, 0
 
 

@@ -152,8 +152,7 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
     minority = 0 if counts[0] <= counts[1] else 1
 
     cache = {}
-    keep = []      # tensors read by side streams stay referenced until the unit is done
-    n_fits = [0]
+    keep = [Xte, yte, pte]     # tensors read by side streams stay referenced until the unit is settled
 
     def nn4(tag, X):
         if tag not in cache:
@@ -223,10 +222,14 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
                 ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
                 keep.append(pred)
             timers.append((ci, e0, e1, e2, forest))
-    for lanes in model_streams.values():
-        for side in lanes:
-            side.synchronize()
-    return n_tr
+    # completion markers instead of a drain: the worker goes on to its next unit and settles this
+    # one (status, timings, frees) later, so its streams never run dry between units
+    events = []
+    for s in [torch.cuda.current_stream()] + [side for lanes in model_streams.values() for side in lanes]:
+        e = torch.cuda.Event()
+        e.record(s)
+        events.append(e)
+    return events, keep
 
 
 def prepare(parsed, configs=None, device=None, n_splits=10):
@@ -275,7 +278,26 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
         n_lanes = int(os.environ.get("F16_LANES", "3"))
         model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
                          for m in MODELS}
-        timers = []
+        util = torch.cuda.Stream(device=device)     # status reads / frees of settled units
+        pending = []
+
+        def settle(item):
+            events, keep, timers = item
+            for e in events:
+                e.synchronize()
+            with torch.cuda.stream(util):
+                for ci, e0, e1, e2, forest in timers:
+                    forest.status()
+                    with lock:
+                        times[ci, 0] += e0.elapsed_time(e1) * 1e-3
+                        times[ci, 1] += e1.elapsed_time(e2) * 1e-3
+                    forest.free()
+            keep.clear()
+            with lock:
+                done[0] += 1
+                if progress:
+                    progress(done[0], len(mine))
+
         try:
             with torch.cuda.stream(stream):
                 while True:
@@ -283,21 +305,15 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
                         u = q.get_nowait()
                     except queue.Empty:
                         break
+                    timers = []
                     with ops.column_order(gd.col_order[u[0]]):
-                        _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators, timers,
-                                  model_streams)
-                    stream.synchronize()
-                    for ci, e0, e1, e2, forest in timers:
-                        forest.status()
-                        with lock:
-                            times[ci, 0] += e0.elapsed_time(e1) * 1e-3
-                            times[ci, 1] += e1.elapsed_time(e2) * 1e-3
-                        forest.free()
-                    timers.clear()
-                    with lock:
-                        done[0] += 1
-                        if progress:
-                            progress(done[0], len(mine))
+                        events, keep = _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators,
+                                                 timers, model_streams)
+                    pending.append((events, keep, timers))
+                    if len(pending) > 1:            # one unit in flight behind the current one
+                        settle(pending.pop(0))
+                while pending:
+                    settle(pending.pop(0))
         except Exception as ex:  # propagate to the caller
             with lock:
                 errors.append(ex)

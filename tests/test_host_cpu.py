@@ -175,3 +175,49 @@ def test_world_size_2_sharding_and_reduce():
     assert sum(sizes) == 120 and abs(sizes[0] - sizes[1]) <= 30
     expect = np.array([sum(f + 1 for f in range(10)) * (ci + 1) for ci in range(216)])
     assert np.array_equal(counts[:, 0, 0], expect)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/experiment.py"), reason="reference tree not present")
+def test_scores_pickle_is_consumed_by_reference_figures(tmp_path):
+    """the reference's own consumers of scores.pkl (get_top_tables,
+    get_comparison_table, write_table - experiment.py:559-586, 621-630, 665-684) accept the dict
+    this repo assembles (same keys, value layout, None handling, numpy.str_ project names)."""
+    import sys
+    import types
+    import samplers_np
+    for name in ("coverage", "shap", "imblearn", "imblearn.over_sampling", "imblearn.combine", "imblearn.under_sampling"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["coverage"].numbits = None
+    sys.modules["shap"].TreeExplainer = None
+    sys.modules["imblearn.over_sampling"].SMOTE = samplers_np.SMOTE
+    sys.modules["imblearn.combine"].SMOTEENN = samplers_np.SMOTEENN
+    sys.modules["imblearn.combine"].SMOTETomek = samplers_np.SMOTETomek
+    sys.modules["imblearn.under_sampling"].TomekLinks = samplers_np.TomekLinks
+    sys.modules["imblearn.under_sampling"].EditedNearestNeighbours = samplers_np.EditedNearestNeighbours
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_experiment", "/root/reference/experiment.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    from flake16_framework_b200 import hostprep as hp, scores as S, synth
+    gold = pickle.load(open(os.path.join(GOLD, "scores_n1500_seed16.pkl"), "rb"))
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(1500, 16))
+    configs = S.all_config_keys()
+    gd = S.GridData(parsed, configs)
+    counts = np.zeros((len(configs), gd.n_proj + 1, 3), dtype=np.int64)
+    for ci, cfg in enumerate(configs):
+        g_proj, g_total = gold[cfg]
+        for pid, name in enumerate(gd.proj_names):
+            counts[ci, pid] = g_proj[str(name)]
+        counts[ci, gd.n_proj] = g_total
+    scores = S.assemble_scores(configs, counts, np.full((len(configs), 2), 0.5), gd)
+
+    tab_nod, tab_od = ref.get_top_tables(scores)
+    assert len(tab_nod[0]) == 10 and len(tab_od[0]) == 10
+    comp = ref.get_comparison_table(scores[("NOD", "FlakeFlagger", "None", "Tomek Links", "Extra Trees")],
+                                    scores[("NOD", "Flake16", "PCA", "SMOTE", "Extra Trees")])
+    assert comp[1][0][0] == "{\\bf Total}" and len(comp[1][0]) == 13
+    os.chdir(tmp_path)
+    ref.write_table("nod-top.tex", tab_nod)
+    ref.write_table("nod-comp.tex", comp)
+    assert open("nod-top.tex").read().count("\\\\") == 10
