@@ -104,8 +104,8 @@ __global__ void k_gather_u8(const uint8_t* __restrict__ y, const int64_t* __rest
 
 extern "C" int f16_gather_rows_f32(const double* X_dev, int32_t d, const int64_t* idx_dev, int64_t n_out,
                                    float* out_dev, void* stream) {
+    if (n_out == 0) return F16_OK;        // empty batch: nothing to stage (pointers may be null)
     if (!X_dev || !out_dev || d < 1 || d > F16_MAX_D || n_out < 0) { f16_set_error("f16_gather_rows_f32: bad arguments"); return F16_ERR_INVALID; }
-    if (n_out == 0) return F16_OK;
     int dp = (d <= 8) ? 8 : 16;
     int64_t tot = n_out * dp;
     k_gather_cast<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X_dev, d, idx_dev, n_out, dp, out_dev);

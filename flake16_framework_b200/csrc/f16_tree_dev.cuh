@@ -146,7 +146,7 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
         }
 #pragma unroll
         for (int j = 0; j < PU; j++) {
-            if (j < nj) left[j] = valid[j] && pred(e[j]);
+            if (j < nj) left[j] = valid[j] && pred(e[j], start + base + j * NT + tid);
         }
 #pragma unroll
         for (int j = 0; j < PU; j++) {

@@ -370,10 +370,15 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                         for (int j = 0; j < 4; j++) { a[j] = __ldg(r0 + fk[j]); b[j] = __ldg(r1 + fk[j]); }
                         unsigned long long one0 = 1ull | ((unsigned long long)f16_y(e0) << 32);
                         unsigned long long one1 = v1 ? (1ull | ((unsigned long long)f16_y(e1) << 32)) : 0ull;
+                        unsigned bits0 = 0, bits1 = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            if ((double)a[j] <= tk[j]) acc[j] += one0;
-                            if ((double)b[j] <= tk[j]) acc[j] += one1;
+                            if ((double)a[j] <= tk[j]) { acc[j] += one0; bits0 |= 1u << j; }
+                            if ((double)b[j] <= tk[j]) { acc[j] += one1; bits1 |= 1u << j; }
+                        }
+                        if (k0 == 0) {          // comparison bits of the first 4 candidates, by position
+                            cmpb[start + i0] = (uint8_t)bits0;
+                            if (v1) cmpb[start + i1] = (uint8_t)bits1;
                         }
                     }
 #pragma unroll
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                     }
                     if (bk >= 0) {
                         int nl = (int)(uint32_t)s_cnt[bk], l1 = (int)(s_cnt[bk] >> 32), l0 = nl - l1;
-                        c.best_f = s_cand_f[bk]; c.best_thr = s_cand_thr[bk];
+                        c.best_f = s_cand_f[bk]; c.best_thr = s_cand_thr[bk]; c.node_id_k = bk;
                         c.n_left = nl; c.l0 = l0; c.l1 = l1;
                         c.split = improvement_ok(l0, l1, c.c0, c.c1, W_total) ? 1 : 0;
                     }
@@ -412,8 +417,15 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
         if (c.done) break;
         if (c.split) {
             const int bf = c.best_f; const double bthr = c.best_thr;
-            block_partition(src, dst, start, nn, c.n_left,
-                            [&](uint32_t e) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
+            if (c.ncand <= 4) {
+                // sweep 2 left one comparison bit per (row, candidate): the partition needs no gather
+                const int bk = c.node_id_k;
+                block_partition(src, dst, start, nn, c.n_left,
+                                [&](uint32_t, int pos) { return (cmpb[pos] >> bk) & 1; }, s_wcnt);
+            } else {
+                block_partition(src, dst, start, nn, c.n_left,
+                                [&](uint32_t e, int) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
+            }
             __syncthreads();
         }
     }
