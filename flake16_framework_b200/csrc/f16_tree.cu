@@ -159,6 +159,7 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
         P.boot_w = bw;
     }
     size_t dyn = 0;
+    if (!best) CUDA_TRY(f16_malloc_async((void**)&P.cmp, (size_t)n_trees * (size_t)n, st));
     if (best) {
         CUDA_TRY(f16_malloc_async((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
         P.side_words = (int)((n + 31) / 32);
@@ -187,14 +188,15 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     if (bw) CUDA_TRY(cudaFreeAsync(bw, st));
     if (P.side_global) CUDA_TRY(cudaFreeAsync(P.side_global, st));
     if (P.lid) CUDA_TRY(cudaFreeAsync(P.lid, st));
+    if (P.cmp) CUDA_TRY(cudaFreeAsync(P.cmp, st));
     *out = F;
     return F16_OK;
 }
 
 extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64_t n, uint8_t* pred_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (F && n == 0) return F16_OK;     // empty batch (pointers may be null)
     if (!F || !X_dev || !pred_dev || n < 0) { f16_set_error("f16_forest_predict: bad arguments"); return F16_ERR_INVALID; }
-    if (n == 0) return F16_OK;
     int2* leaf = nullptr;
     CUDA_TRY(f16_malloc_async((void**)&leaf, sizeof(int2) * (size_t)F->n_trees * n, st));
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)F->n_trees);

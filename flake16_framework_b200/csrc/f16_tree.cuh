@@ -37,6 +37,7 @@ struct F16FitParams {
     int32_t* node_count;        // [n_trees]
     uint32_t* side_global;      // [n_trees][ceil(n/32)] or nullptr (side bits live in smem)
     uint32_t* lid;              // best: [n_trees][n] global row id -> local id of the relocated node
+    uint8_t* cmp;               // random: [n_trees][n] comparison bits of the candidate sweep, by position
     int32_t* err;               // device error flag
     int n, d, dp, n_trees, max_features, stack_cap, node_cap, side_words;
 };

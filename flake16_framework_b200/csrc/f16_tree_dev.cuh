@@ -34,6 +34,7 @@ struct Ctl {
     int n_const_out;
     uint32_t const_mask_out;
     int node_id;
+    int node_id_k;          // index of the winning candidate within the first chunk (ET)
     unsigned long long win_key;
     int sp, node_count;
 };

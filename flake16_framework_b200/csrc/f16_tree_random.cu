@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     const float* __restrict__ X = P.X;
     uint32_t* buf0 = P.buf + (size_t)t * 2 * n;
     uint32_t* buf1 = buf0 + n;
+    uint8_t* cmpb = P.cmp + (size_t)t * n;
     F16Node* nodes = P.nodes + (size_t)t * P.node_cap;
     TreeStack stk;
     stk.smem = s_stack;
