@@ -159,7 +159,6 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
         P.boot_w = bw;
     }
     size_t dyn = 0;
-    if (!best) CUDA_TRY(f16_malloc_async((void**)&P.cmp, (size_t)n_trees * (size_t)n, st));
     if (best) {
         CUDA_TRY(f16_malloc_async((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
         P.side_words = (int)((n + 31) / 32);

@@ -206,7 +206,6 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     const float* __restrict__ X = P.X;
     uint32_t* buf0 = P.buf + (size_t)t * 2 * n;
     uint32_t* buf1 = buf0 + n;
-    uint8_t* cmpb = P.cmp + (size_t)t * n;
     F16Node* nodes = P.nodes + (size_t)t * P.node_cap;
     TreeStack stk;
     stk.smem = s_stack;
@@ -371,15 +370,10 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                         for (int j = 0; j < 4; j++) { a[j] = __ldg(r0 + fk[j]); b[j] = __ldg(r1 + fk[j]); }
                         unsigned long long one0 = 1ull | ((unsigned long long)f16_y(e0) << 32);
                         unsigned long long one1 = v1 ? (1ull | ((unsigned long long)f16_y(e1) << 32)) : 0ull;
-                        unsigned bits0 = 0, bits1 = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            if ((double)a[j] <= tk[j]) { acc[j] += one0; bits0 |= 1u << j; }
-                            if ((double)b[j] <= tk[j]) { acc[j] += one1; bits1 |= 1u << j; }
-                        }
-                        if (k0 == 0) {          // comparison bits of the first 4 candidates, by position
-                            cmpb[start + i0] = (uint8_t)bits0;
-                            if (v1) cmpb[start + i1] = (uint8_t)bits1;
+                            if ((double)a[j] <= tk[j]) acc[j] += one0;
+                            if ((double)b[j] <= tk[j]) acc[j] += one1;
                         }
                     }
 #pragma unroll
@@ -418,15 +412,10 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
         if (c.done) break;
         if (c.split) {
             const int bf = c.best_f; const double bthr = c.best_thr;
-            if (c.ncand <= 4) {
-                // sweep 2 left one comparison bit per (row, candidate): the partition needs no gather
-                const int bk = c.node_id_k;
-                block_partition(src, dst, start, nn, c.n_left,
-                                [&](uint32_t, int pos) { return (cmpb[pos] >> bk) & 1; }, s_wcnt);
-            } else {
-                block_partition(src, dst, start, nn, c.n_left,
-                                [&](uint32_t e, int) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
-            }
+            // (storing the candidate sweep's comparison bits per row and partitioning from them,
+            //  without this gather, was measured 15 % SLOWER: extra byte stores + register spills)
+            block_partition(src, dst, start, nn, c.n_left,
+                            [&](uint32_t e, int) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
             __syncthreads();
         }
     }
