@@ -30,155 +30,6 @@ template <> struct SubCfg<16> { static constexpr int S = F16_S16; };
 template <> struct SubCfg<8> { static constexpr int S = F16_S8; };
 #define k_build_random F16_CAT(k_build_random, F16_VARIANT)
 
-// ------------------------------------------------------------------ SHARED regime (warp 0)
-template <int DP>
-__device__ void subtree_warp(Ctl& c, DrawState& ds, const TreeStack& stk, const F16FitParams& P, F16Node* nodes,
-                             const float* s_col, uint16_t (*s_idx)[SubCfg<DP>::S], const uint8_t* s_y,
-                             int* s_cand_f, double* s_cand_thr) {
-    constexpr int S = SubCfg<DP>::S;
-    constexpr int SP = S + 1;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const double W_total = (double)P.n;
-    int sp = c.sp, node_count = c.node_count;
-    uint32_t rng = ds.rng;
-    const int d = P.d, max_features = P.max_features;
-
-    while (sp > 0) {
-        F16StackRec r = stk.get(sp - 1);
-        if (!r.pad) break;                      // back to a node that lives in global memory
-        sp--;
-        const int start = r.start, nn = r.end - r.start;
-        const int par = r.depth & 1;
-        const uint16_t* idx = s_idx[par] + start;
-        const int t0 = r.c0, t1 = r.c1;
-        bool split = false;
-        int best_f = -2, n_left = 0, bl0 = 0, bl1 = 0;
-        double best_thr = -2.0;
-        int n_total = r.n_const;
-        uint32_t cmask = r.const_mask;
-
-        if (!leaf_pretest(nn, t0, t1)) {
-            // ---- feature draw; every lane runs the scalar loop on its own copy of the state,
-            //      lane 0 applies the swaps to the shared permutation
-            int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0, ncand = 0;
-            const int n_known = r.n_const;
-            while (f_i > n_total && (n_visited < max_features || n_visited <= n_found + n_drawn)) {
-                n_visited++;
-                int f_j = f16_rand_int(n_drawn, f_i - n_found, &rng);
-                if (f_j < n_known) {
-                    int a = ds.features[n_drawn], b = ds.features[f_j];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[n_drawn] = b; ds.features[f_j] = a; }
-                    __syncwarp();
-                    n_drawn++;
-                    continue;
-                }
-                f_j += n_found;
-                const int f = ds.features[f_j];
-                float mn = INFINITY, mx = -INFINITY;
-                for (int i = lane; i < nn; i += 32) {
-                    float v = s_col[f * SP + idx[i]];
-                    mn = fminf(mn, v); mx = fmaxf(mx, v);
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    mn = fminf(mn, __shfl_xor_sync(F16_FULL, mn, off));
-                    mx = fmaxf(mx, __shfl_xor_sync(F16_FULL, mx, off));
-                }
-                if (mx <= __fadd_rn(mn, 1e-7f)) {
-                    int b = ds.features[n_total];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[f_j] = b; ds.features[n_total] = f; }
-                    __syncwarp();
-                    n_found++; n_total++;
-                    continue;
-                }
-                f_i--;
-                {
-                    int b = ds.features[f_i];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[f_i] = f; ds.features[f_j] = b; }
-                    __syncwarp();
-                }
-                double thr = f16_rand_uniform((double)mn, (double)mx, &rng);
-                if (thr == (double)mx) thr = (double)mn;
-                if (lane == 0) { s_cand_f[ncand] = f; s_cand_thr[ncand] = thr; }
-                ncand++;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];
-                for (int i = n_known; i < n_total; i++) ds.const_feats[i] = ds.features[i];
-            }
-            __syncwarp();
-            for (int i = n_known; i < n_total; i++) cmask |= 1u << ds.const_feats[i];
-
-            // ---- evaluate the candidates (strict >, first wins)
-            double best = -INFINITY;
-            for (int k = 0; k < ncand; k++) {
-                const int f = s_cand_f[k];
-                const double thr = s_cand_thr[k];
-                int nl = 0, l1 = 0;
-                for (int base = 0; base < nn; base += 32) {
-                    int i = base + lane;
-                    bool valid = i < nn;
-                    int li = valid ? idx[i] : 0;
-                    bool left = valid && ((double)s_col[f * SP + li] <= thr);
-                    unsigned bal = __ballot_sync(F16_FULL, left);
-                    unsigned by = __ballot_sync(F16_FULL, left && s_y[li]);
-                    nl += __popc(bal); l1 += __popc(by);
-                }
-                double proxy = gini_proxy(nl - l1, l1, t0, t1);
-                if (proxy > best) { best = proxy; best_f = f; best_thr = thr; n_left = nl; bl1 = l1; bl0 = nl - l1; }
-            }
-            if (best_f >= 0) split = improvement_ok(bl0, bl1, t0, t1, W_total);
-        }
-
-        // ---- node record
-        const int id = node_count++;
-        if (id >= P.node_cap || sp + 2 > P.stack_cap) { if (lane == 0) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; } break; }
-        if (lane == 0) {
-            F16Node nd;
-            nd.thr = split ? best_thr : -2.0;
-            nd.feature = split ? best_f : -2;
-            nd.right = -1;
-            nd.c0 = t0; nd.c1 = t1; nd.n = nn; nd.depth = r.depth;
-            nodes[id] = nd;
-            if (r.parent >= 0 && !r.is_left) nodes[r.parent].right = id;
-        }
-        if (split) {
-            // ---- stable partition idx[par] -> idx[par ^ 1]
-            uint16_t* out = s_idx[par ^ 1] + start;
-            int run_l = 0;
-            for (int base = 0; base < nn; base += 32) {
-                int i = base + lane;
-                bool valid = i < nn;
-                int li = valid ? idx[i] : 0;
-                bool left = valid && ((double)s_col[best_f * SP + li] <= best_thr);
-                unsigned bal = __ballot_sync(F16_FULL, left);
-                int lrank = __popc(bal & lt);
-                if (valid) {
-                    if (left) out[run_l + lrank] = (uint16_t)li;
-                    else out[n_left + (base - run_l) + (lane - lrank)] = (uint16_t)li;
-                }
-                run_l += __popc(bal);
-            }
-            if (lane == 0) {
-                F16StackRec q;
-                q.parent = id; q.depth = r.depth + 1; q.n_const = (int16_t)n_total; q.const_mask = cmask; q.pad = 1;
-                q.start = start + n_left; q.end = r.end; q.c0 = t0 - bl0; q.c1 = t1 - bl1; q.is_left = 0;
-                stk.put(sp, q);
-                q.start = start; q.end = start + n_left; q.c0 = bl0; q.c1 = bl1; q.is_left = 1;
-                stk.put(sp + 1, q);
-            }
-            sp += 2;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) { c.sp = sp; c.node_count = node_count; ds.rng = rng; }
-}
-
 // ------------------------------------------------------------------ kernel
 template <int DP>
 __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
