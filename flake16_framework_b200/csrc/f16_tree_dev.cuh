@@ -85,9 +85,12 @@ __device__ __forceinline__ bool improvement_ok(int l0, int l1, int t0, int t1, d
 }
 
 // the builder's leaf pre-test (_tree.pyx:223-240): n_node_samples < 2 or impurity <= EPSILON
+// `impurity <= EPSILON` is decided without the float64 division: the class sums are integers
+// below 2^24 (row-id limit), so for a pure node sq == w*w exactly and the Gini evaluates to
+// exactly 0, while an impure node has Gini = 2 c0 c1 / w^2 >= 2 (w - 1) / w^2 > 1e-7, twelve
+// orders of magnitude above EPSILON and its rounding error.
 __device__ __forceinline__ bool leaf_pretest(int n_node, int c0, int c1) {
-    double wn = (double)c0 + (double)c1;
-    return (n_node < 2) || (gini_of((double)c0, (double)c1, wn) <= F16_EPS);
+    return (n_node < 2) || (c0 == 0) || (c1 == 0);
 }
 
 // one thread: write node, link to parent, push children (right first: left is popped first)

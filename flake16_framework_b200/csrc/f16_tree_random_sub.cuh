@@ -64,7 +64,22 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
             const int n_known = r.n_const;
             int cf[4] = {0, 0, 0, 0};
             double ct[4] = {0.0, 0.0, 0.0, 0.0};
+            float clo[4] = {0.f, 0.f, 0.f, 0.f}, chi[4] = {0.f, 0.f, 0.f, 0.f};
+            double cr[4] = {0.0, 0.0, 0.0, 0.0};
             double best = -INFINITY;
+
+            // rand_uniform's arithmetic (sklearn/tree/_utils.pyx:57-61), candidate j on lane j:
+            // ((high - low) * r / RAND_R_MAX) + low ; threshold == max -> min (_splitter.pyx:652-653)
+            auto finish_thresholds = [&]() {
+                const int j = lane & 3;
+                float lo = clo[0], hi = chi[0]; double r = cr[0];
+#pragma unroll
+                for (int m = 1; m < 4; m++) if (j == m) { lo = clo[m]; hi = chi[m]; r = cr[m]; }
+                double thr = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)hi, (double)lo), r), 2147483647.0), (double)lo);
+                if (thr == (double)hi) thr = (double)lo;
+#pragma unroll
+                for (int m = 0; m < 4; m++) ct[m] = __shfl_sync(F16_FULL, thr, m);
+            };
 
             auto eval_chunk = [&](int cnt) {
                 int nl[4] = {0, 0, 0, 0}, l1[4] = {0, 0, 0, 0};
@@ -130,14 +145,15 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
                     if (lane == 0) { ds.features[f_i] = f; ds.features[f_j] = b; }
                     __syncwarp();
                 }
-                double thr = f16_rand_uniform((double)fmn, (double)fmx, &rng);
-                if (thr == (double)fmx) thr = (double)fmn;
+                // the draw consumes the generator now; the float64 division of rand_uniform is
+                // deferred so that the (up to 4) thresholds of a chunk are divided on 4 lanes at once
+                const double rr = (double)f16_rand_r(&rng);
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (j == ncand) { cf[j] = f; ct[j] = thr; }
+                for (int j = 0; j < 4; j++) if (j == ncand) { cf[j] = f; clo[j] = fmn; chi[j] = fmx; cr[j] = rr; }
                 ncand++;
-                if (ncand == 4) { eval_chunk(4); ncand = 0; }
+                if (ncand == 4) { finish_thresholds(); eval_chunk(4); ncand = 0; }
             }
-            if (ncand > 0) eval_chunk(ncand);
+            if (ncand > 0) { finish_thresholds(); eval_chunk(ncand); }
             __syncwarp();
             if (lane == 0) {
                 for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];

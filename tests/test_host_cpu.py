@@ -221,3 +221,26 @@ def test_scores_pickle_is_consumed_by_reference_figures(tmp_path):
     ref.write_table("nod-top.tex", tab_nod)
     ref.write_table("nod-comp.tex", comp)
     assert open("nod-top.tex").read().count("\\\\") == 10
+
+
+def test_abi_argument_validation_without_gpu():
+    """Limits are enforced before any CUDA call (maximum sizes, dimensions, k): safe to check on CPU
+    with dummy non-null pointers that are never dereferenced."""
+    from flake16_framework_b200 import _lib
+    L = _lib.lib()
+    fake = ctypes.c_void_p(0x1000)
+    h = ctypes.c_void_p()
+    # n at / above the 24-bit row-id limit, d above 16, bad kind, bad max_features
+    assert L.f16_forest_fit(fake, fake, 1 << 24, 16, fake, 1, 100, 4, 0, None, ctypes.byref(h)) == -1
+    assert b"bad arguments" in L.f16_last_error()
+    assert L.f16_forest_fit(fake, fake, 1000, 17, fake, 1, 100, 4, 0, None, ctypes.byref(h)) == -1
+    assert L.f16_forest_fit(fake, fake, 1000, 16, fake, 7, 100, 4, 0, None, ctypes.byref(h)) == -1
+    assert L.f16_forest_fit(fake, fake, 1000, 16, fake, 1, 100, 17, 0, None, ctypes.byref(h)) == -1
+    assert L.f16_forest_fit(fake, fake, 1000, 16, None, 1, 100, 4, 0, None, ctypes.byref(h)) == -1   # RF needs sorted_idx
+    assert b"sorted_idx" in L.f16_last_error()
+    assert L.f16_knn(fake, 100, fake, 100, 16, 9, None, 0, fake, None) == -1                            # k > 8
+    assert L.f16_knn(fake, 3, fake, 3, 16, 4, None, 0, fake, None) == -1                                # k > n
+    bad_order = (ctypes.c_int32 * 16)(*([0] * 16))
+    assert L.f16_knn(fake, 100, fake, 100, 16, 4, bad_order, 0, fake, None) == -1                       # not a permutation
+    assert L.f16_confusion(fake, fake, fake, 10, 0, fake, None) == -1
+    assert L.f16_tree_seeds(0, 1, 0, fake, fake) == -1
