@@ -36,7 +36,7 @@ def _sources(tune):
                                       "-DF16_MINB=%d" % t["DT_MINB"]]),
         ("f16_misc.cu", "", ["-fmad=false"]),
         ("f16_sort.cu", "", []),
-        ("f16_knn.cu", "", []),
+        ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
         ("f16_knn32.cu", "", []),
     )
 

@@ -81,7 +81,12 @@ __device__ __forceinline__ void knn_cp_wait_all() { asm volatile("cp.async.wait_
 
 // Each thread owns KQ = 2 queries (registers), so every 16-byte shared-memory load of a
 // reference row feeds 4 DFMAs: the kernel stays bound by the FP64 pipe, not by LDS issue.
+#ifndef KQ
 #define KQ 2
+#endif
+#ifndef KNN_UNROLL
+#define KNN_UNROLL 1
+#endif
 // PREFIX: test the two leading (highest-variance) coordinates first and skip the rest of the
 // row when no lane of the warp can improve - pays off when those columns dominate the distance
 // (raw, unscaled features); without it the row is one uninterrupted DFMA stream.
@@ -126,6 +131,8 @@ __global__ void __launch_bounds__(KT) k_knn(const double* __restrict__ A, int n,
             knn_cp_commit();
         }
         const double* tile = tiles[buf];
+        constexpr int kRowUnroll = KNN_UNROLL;
+#pragma unroll kRowUnroll
         for (int j = 0; j < cnt; j++) {
             const double2* t2 = reinterpret_cast<const double2*>(tile + j * TS);
             const double2 nn = t2[0];
