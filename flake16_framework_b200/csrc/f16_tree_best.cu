@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
     uint32_t* side = P.side_global ? P.side_global + (size_t)t * P.side_words : s_side_dyn;
     const uint8_t* bw = P.boot_w ? P.boot_w + (size_t)t * (((size_t)n + 3) / 4 * 4) : nullptr;
     const double W_total = (double)n;   // sum of bootstrap counts == n; unit weights == n
+    PH_DECL
 
     // ---- root: per feature, compact the column argsort to the in-bag rows (weight > 0),
     //      packing (id, weight, label).  A warp owns a feature.
@@ -235,11 +236,12 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
         F16StackRec r;
         r.start = 0; r.end = s_cntn[0]; r.parent = -1; r.c0 = (int)(uint32_t)tot; r.c1 = (int)(tot >> 32);
         r.const_mask = 0; r.n_const = 0; r.is_left = 0; r.pad = 0; r.depth = 0;
-        c.sp = 0; c.node_count = 0; c.done = 0;
+        c.sp = 0; c.node_count = 0; c.done = 0; c.abort = 0; c.split = 0;
         stk.put(c.sp++, r);
     }
     __syncthreads();
 
+    PH_T(1, 0);
     while (true) {
         if (tid == 0) pop_node(c, stk);
         __syncthreads();
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             }
             if (tid == 0) { c.in_smem = 1; c.start = 0; c.end = nn; }
             __syncthreads();
+            PH_T(1, 1);
         }
         const bool sm = c.in_smem != 0;
         const int start = c.start;
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 c.ncand = ne; c.n_const_out = n_total; c.const_mask_out = m;
             }
             __syncthreads();
+            PH_T(1, sm ? 5 : 2);
             n_eval = c.ncand;
             // ---- candidate scan: warp w owns evaluated features w, w+NW, ...
             BestCand best;
@@ -401,11 +405,12 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     c.split = improvement_ok(best.l0, best.l1, t0, t1, W_total) ? 1 : 0;
                 }
                 __syncthreads();
+                PH_T(1, sm ? 6 : 3);
             }
         }
         if (tid == 0) finish_node(c, P, nodes, stk);
         __syncthreads();
-        if (c.done) break;
+        if (c.abort) break;
         if (c.split) {
             // ---- mark the side of every row of the node (the winning feature's slice is
             //      sorted, so the left rows are its first n_left entries)
@@ -424,10 +429,16 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 warp_partition(src + (size_t)f * stride, dst + (size_t)f * stride, start, nn, n_left, nside);
             }
             __syncthreads();
+            if (tid == 0) c.split = 0;
+            PH_T(1, sm ? 7 : 4);
+        } else {
+            PH_T(1, sm ? 9 : 8);
         }
     }
     if (tid == 0) P.node_count[t] = c.node_count;
 }
+
+F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))
 
 int F16_CAT(f16_launch_build_best, F16_VARIANT)(const F16FitParams& P, size_t dyn_smem, cudaStream_t st) {
     cudaError_t e;

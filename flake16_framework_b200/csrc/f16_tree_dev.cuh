@@ -26,7 +26,10 @@ struct Ctl {
     int start, end, parent, c0, c1, n_const, is_left, depth;
     uint32_t const_mask;
     int in_smem;
-    int done, leaf, split;
+    // done: written by pop_node only; abort: written by the node writers only; split: set by the
+    // winner, cleared by the split path itself - so no flag is rewritten while a slower warp
+    // may still be reading it after the last barrier of an iteration
+    int done, abort, leaf, split;
     int ncand;
     int best_f;
     double best_thr;
@@ -96,7 +99,7 @@ __device__ __forceinline__ bool leaf_pretest(int n_node, int c0, int c1) {
 // one thread: write node, link to parent, push children (right first: left is popped first)
 __device__ __forceinline__ void finish_node(Ctl& c, const F16FitParams& P, F16Node* nodes, const TreeStack& stk) {
     int id = c.node_count++;
-    if (id >= P.node_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; return; }
+    if (id >= P.node_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.abort = 1; return; }
     F16Node nd;
     nd.thr = c.split ? c.best_thr : -2.0;
     nd.feature = c.split ? c.best_f : -2;
@@ -106,7 +109,7 @@ __device__ __forceinline__ void finish_node(Ctl& c, const F16FitParams& P, F16No
     if (c.parent >= 0 && !c.is_left) nodes[c.parent].right = id;
     c.node_id = id;
     if (c.split) {
-        if (c.sp + 2 > P.stack_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; return; }
+        if (c.sp + 2 > P.stack_cap) { atomicExch(P.err, F16_ERR_OVERFLOW); c.abort = 1; return; }
         F16StackRec r;
         r.parent = id; r.depth = c.depth + 1; r.n_const = (int16_t)c.n_const_out;
         r.const_mask = c.const_mask_out; r.pad = (uint8_t)c.in_smem;
@@ -125,7 +128,7 @@ __device__ __forceinline__ void pop_node(Ctl& c, const TreeStack& stk) {
     c.n_const = r.n_const; c.const_mask = r.const_mask; c.is_left = r.is_left; c.depth = r.depth;
     c.in_smem = r.pad;
     c.leaf = leaf_pretest(r.end - r.start, r.c0, r.c1);
-    c.split = 0; c.ncand = 0;
+    c.ncand = 0;
     c.n_const_out = r.n_const; c.const_mask_out = r.const_mask;
 }
 
@@ -176,6 +179,28 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
         }
     }
 }
+
+// Optional per-phase cycle accounting of the tree builders (tools/phase_probe.py builds a
+// variant with -DF16_PHASE_TIMING; the product library is compiled without it).
+#ifdef F16_PHASE_TIMING
+#define F16_NPH 12
+static __device__ unsigned long long f16_phase_cycles[2][F16_NPH];   // one copy per translation unit
+static __device__ unsigned long long f16_phase_nodes[2][F16_NPH];
+#define F16_PHASE_READER(name) extern "C" int name(unsigned long long* cycles, unsigned long long* nodes, int reset) { \
+    if (cudaMemcpyFromSymbol(cycles, f16_phase_cycles, sizeof(f16_phase_cycles)) != cudaSuccess) return 1; \
+    if (cudaMemcpyFromSymbol(nodes, f16_phase_nodes, sizeof(f16_phase_nodes)) != cudaSuccess) return 1; \
+    if (reset) { unsigned long long z[2][F16_NPH] = {}; cudaMemcpyToSymbol(f16_phase_cycles, z, sizeof(z)); \
+                 cudaMemcpyToSymbol(f16_phase_nodes, z, sizeof(z)); } \
+    return 0; }
+#define PH_DECL long long ph_last = clock64();
+#define PH_T(kind, k) do { if (threadIdx.x == 0) { long long ph_now = clock64(); \
+    atomicAdd(&f16_phase_cycles[kind][k], (unsigned long long)(ph_now - ph_last)); \
+    atomicAdd(&f16_phase_nodes[kind][k], 1ull); ph_last = ph_now; } } while (0)
+#else
+#define PH_DECL
+#define PH_T(kind, k) do { } while (0)
+#define F16_PHASE_READER(name)
+#endif
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
 int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);

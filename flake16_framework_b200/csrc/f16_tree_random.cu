@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     stk.smem = s_stack;
     stk.gmem = P.stack + (size_t)t * P.stack_cap;
     const double W_total = (double)n;
+    PH_DECL
 
     // ---- root: identity sample list with packed labels; class counts
     unsigned long long cnt = 0;
@@ -81,10 +82,11 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
         F16StackRec r;
         r.start = 0; r.end = n; r.parent = -1; r.c0 = (int)(uint32_t)tot; r.c1 = (int)(tot >> 32);
         r.const_mask = 0; r.n_const = 0; r.is_left = 0; r.pad = 0; r.depth = 0;
-        c.sp = 0; c.node_count = 0; c.done = 0;
+        c.sp = 0; c.node_count = 0; c.done = 0; c.abort = 0; c.split = 0;
         stk.put(c.sp++, r);
     }
     __syncthreads();
+    PH_T(0, 0);
 
     while (true) {
         if (tid == 0) pop_node(c, stk);
@@ -116,9 +118,11 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                 stk.put(c.sp++, r);
             }
             __syncthreads();
+            PH_T(0, 1);
             if (warp == 0) subtree_warp_v2<DP, S>(c, ds, stk, P, nodes, s_col, s_idx, s_y);
             __syncthreads();
-            if (c.done) break;
+            PH_T(0, 5);
+            if (c.abort) break;
             continue;
         }
 
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                 c.ncand = ncand; c.n_const_out = n_total; c.const_mask_out = m;
             }
             __syncthreads();
+            PH_T(0, 2);
             const int ncand = c.ncand;
             if (ncand > 0) {
                 // ---- pass 2: left counts of every candidate threshold (4 candidates per sweep)
@@ -260,7 +265,8 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
         }
         if (tid == 0) finish_node(c, P, nodes, stk);
         __syncthreads();
-        if (c.done) break;
+        PH_T(0, c.leaf ? 6 : 3);
+        if (c.abort) break;
         if (c.split) {
             const int bf = c.best_f; const double bthr = c.best_thr;
             // (storing the candidate sweep's comparison bits per row and partitioning from them,
@@ -268,10 +274,14 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
             block_partition(src, dst, start, nn, c.n_left,
                             [&](uint32_t e, int) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
             __syncthreads();
+            if (tid == 0) c.split = 0;
+            PH_T(0, 4);
         }
     }
     if (tid == 0) P.node_count[t] = c.node_count;
 }
+
+F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))
 
 int F16_CAT(f16_launch_build_random, F16_VARIANT)(const F16FitParams& P, cudaStream_t st) {
     if (P.dp == 8) k_build_random<8><<<P.n_trees, NT, 0, st>>>(P);

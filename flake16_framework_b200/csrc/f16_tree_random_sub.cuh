@@ -182,7 +182,7 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
 
         // ---- node record
         const int id = node_count++;
-        if (id >= P.node_cap || sp + 2 > P.stack_cap) { if (lane == 0) { atomicExch(P.err, F16_ERR_OVERFLOW); c.done = 1; } break; }
+        if (id >= P.node_cap || sp + 2 > P.stack_cap) { if (lane == 0) { atomicExch(P.err, F16_ERR_OVERFLOW); c.abort = 1; } break; }
         if (lane == 0) {
             F16Node nd;
             nd.thr = split ? best_thr : -2.0;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32, 32) k_build_random_w(F16FitParams P) {
     if (lane == 0) {
         for (int f = 0; f < F16_MAX_D; f++) { ds.features[f] = f; ds.const_feats[f] = 0; }
         ds.rng = P.rand_r_state[t];
-        c.done = 0;
+        c.done = 0; c.abort = 0;
     }
     __syncwarp();
     // registers mirror the scalar state; every lane holds the same values
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32, 32) k_build_random_w(F16FitParams P) {
             subtree_warp_v2<DP, S>(c, ds, stk, P, nodes, s_col, s_idx, s_y);
             __syncwarp();
             sp = c.sp; node_count = c.node_count; rng = ds.rng;
-            if (c.done) break;
+            if (c.abort) break;
             continue;
         }
         sp--;
