@@ -206,38 +206,36 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
             PH_T(0, 2);
             const int ncand = c.ncand;
             if (ncand > 0) {
-                // ---- pass 2: left counts of every candidate threshold (4 candidates per sweep)
+                // ---- pass 2: left counts of every candidate threshold, 4 candidates per sweep.
+                //      Four threads share a row: thread t loads the 16-byte quarter of the row that
+                //      holds candidate t's feature, so a warp's load touches 8 rows = 8 lines (four
+                //      scalar gathers per row cost four times the L1 wavefronts).  `x <= thr` for a
+                //      float32 x and a float64 thr is decided in float32 against thr rounded down.
                 for (int k0 = 0; k0 < ncand; k0 += 4) {
-                    int fk[4]; double tk[4];
-                    unsigned long long acc[4];
+                    const int t4 = tid & 3;
+                    const int k = (k0 + t4 < ncand) ? k0 + t4 : k0;
+                    const int fk = s_cand_f[k];
+                    const float tk = __double2float_rd(s_cand_thr[k]);
+                    const int qk = fk >> 2, ck = fk & 3;
+                    unsigned long long acc = 0;
+                    constexpr int RPS = NT / 4;                 // rows per sweep step
+                    for (int i0 = tid >> 2; i0 < nn; i0 += RPS * 4) {
+                        uint32_t e[4]; float4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        int k = (k0 + j < ncand) ? k0 + j : k0;
-                        fk[j] = s_cand_f[k]; tk[j] = s_cand_thr[k]; acc[j] = 0;
-                    }
-                    for (int i0 = tid; i0 < nn; i0 += NT * 2) {
-                        const int i1 = i0 + NT;
-                        const bool v1 = i1 < nn;
-                        uint32_t e0 = src[start + i0], e1 = v1 ? src[start + i1] : 0u;
-                        const float* r0 = X + (size_t)f16_id(e0) * DP;
-                        const float* r1 = X + (size_t)f16_id(e1) * DP;
-                        float a[4], b[4];
+                        for (int u = 0; u < 4; u++) { int i = i0 + u * RPS; e[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
 #pragma unroll
-                        for (int j = 0; j < 4; j++) { a[j] = __ldg(r0 + fk[j]); b[j] = __ldg(r1 + fk[j]); }
-                        unsigned long long one0 = 1ull | ((unsigned long long)f16_y(e0) << 32);
-                        unsigned long long one1 = v1 ? (1ull | ((unsigned long long)f16_y(e1) << 32)) : 0ull;
+                        for (int u = 0; u < 4; u++)
+                            v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)f16_id(e[u] == 0xffffffffu ? 0u : e[u]) * DP) + qk);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if ((double)a[j] <= tk[j]) acc[j] += one0;
-                            if ((double)b[j] <= tk[j]) acc[j] += one1;
+                        for (int u = 0; u < 4; u++) {
+                            const float x = ck == 0 ? v[u].x : ck == 1 ? v[u].y : ck == 2 ? v[u].z : v[u].w;
+                            if (e[u] != 0xffffffffu && x <= tk) acc += 1ull | ((unsigned long long)f16_y(e[u]) << 32);
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc[j] = f16_warp_sum_u64(acc[j]);
-                    if (lane == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) s_part[warp][j] = acc[j];
-                    }
+                    acc += __shfl_xor_sync(F16_FULL, acc, 4);
+                    acc += __shfl_xor_sync(F16_FULL, acc, 8);
+                    acc += __shfl_xor_sync(F16_FULL, acc, 16);
+                    if (lane < 4) s_part[warp][lane] = acc;
                     __syncthreads();
                     if (tid < 4 && k0 + tid < ncand) {
                         unsigned long long s = 0;
@@ -268,11 +266,11 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
         PH_T(0, c.leaf ? 6 : 3);
         if (c.abort) break;
         if (c.split) {
-            const int bf = c.best_f; const double bthr = c.best_thr;
+            const int bf = c.best_f; const float bthr = __double2float_rd(c.best_thr);
             // (storing the candidate sweep's comparison bits per row and partitioning from them,
             //  without this gather, was measured 15 % SLOWER: extra byte stores + register spills)
             block_partition(src, dst, start, nn, c.n_left,
-                            [&](uint32_t e, int) { return (double)__ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
+                            [&](uint32_t e, int) { return __ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
             __syncthreads();
             if (tid == 0) c.split = 0;
             PH_T(0, 4);

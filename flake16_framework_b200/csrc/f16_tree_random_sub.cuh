@@ -64,6 +64,7 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
             const int n_known = r.n_const;
             int cf[4] = {0, 0, 0, 0};
             double ct[4] = {0.0, 0.0, 0.0, 0.0};
+            float ctf[4] = {0.f, 0.f, 0.f, 0.f};     // thresholds rounded down: x <= ct  <=>  x <= ctf for float32 x
             float clo[4] = {0.f, 0.f, 0.f, 0.f}, chi[4] = {0.f, 0.f, 0.f, 0.f};
             double cr[4] = {0.0, 0.0, 0.0, 0.0};
             double best = -INFINITY;
@@ -78,7 +79,7 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
                 double thr = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)hi, (double)lo), r), 2147483647.0), (double)lo);
                 if (thr == (double)hi) thr = (double)lo;
 #pragma unroll
-                for (int m = 0; m < 4; m++) ct[m] = __shfl_sync(F16_FULL, thr, m);
+                for (int m = 0; m < 4; m++) { ct[m] = __shfl_sync(F16_FULL, thr, m); ctf[m] = __double2float_rd(ct[m]); }
             };
 
             auto eval_chunk = [&](int cnt) {
@@ -91,7 +92,7 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         if (k < cnt) {
-                            bool left = valid && ((double)s_col[cf[k] * SP + li] <= ct[k]);
+                            bool left = valid && (s_col[cf[k] * SP + li] <= ctf[k]);
                             unsigned bal = __ballot_sync(F16_FULL, left);
                             nl[k] += __popc(bal); l1[k] += __popc(bal & ym);
                         }
@@ -196,12 +197,13 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
             // ---- stable partition idx[par] -> idx[par ^ 1]
             uint16_t* out = s_idx[par ^ 1] + start;
             const float* col = s_col + best_f * SP;
+            const float best_thr_f = __double2float_rd(best_thr);
             int run_l = 0;
             for (int base = 0; base < nn; base += 32) {
                 int i = base + lane;
                 bool valid = i < nn;
                 int li = valid ? idx[i] : 0;
-                bool left = valid && ((double)col[li] <= best_thr);
+                bool left = valid && (col[li] <= best_thr_f);
                 unsigned bal = __ballot_sync(F16_FULL, left);
                 int lrank = __popc(bal & lt);
                 if (valid) {
