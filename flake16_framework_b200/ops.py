@@ -199,6 +199,8 @@ def variance_order(X):
     """(columns of a host matrix by descending variance, filter mode) for ``f16_knn``:
     mode 1 - float64 filter with the early exit on the two leading columns, when they carry most
              of the total variance (raw, unscaled features);
+    mode 3 - tensor-core candidate filter + exact float64 selection, for data of moderate range
+             (StandardScaler / PCA outputs; every |value| <= 3e4 so the float16 x 3 split holds);
     mode 0 - plain float64 filter otherwise.
     (mode 2, a float32 filter for centred data, exists in the library and is covered by the parity
     tests, but is never selected: measured no faster than mode 0 on B200 - a 3-register FFMA
@@ -211,7 +213,17 @@ def variance_order(X):
     tot = float(var.sum())
     if tot > 0 and float(var[order[:2]].sum()) / tot > 0.8:
         return order, 1
+    if X.size and float(np.abs(X).max()) <= 3.0e4:
+        return order, 3
     return order, 0
+
+
+def knn_tc_probe(A, Q):
+    """Largest observed relative error of the tensor-core distance estimate (test hook)."""
+    L = _ready()
+    err = ctypes.c_float(0.0)
+    check(L.f16_knn_tc_probe(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], ctypes.byref(err), _stream()))
+    return float(err.value)
 
 
 def knn(A, Q, k, col_order=None):

@@ -96,10 +96,19 @@ void f16_forest_free(f16_forest* forest, void* stream);
  * Exact float64 brute-force k-NN (NearestNeighbors(k).fit(A).kneighbors(Q)); idx_dev int32
  * [nq][k], ordered by (distance, index).  k <= 8, d <= 16.  col_order (HOST pointer, d ints, or
  * NULL) is the order in which coordinates are accumulated: highest-variance columns first make
- * the partial-distance early exit effective; prefix_test != 0 enables that early exit (worth it
- * when the two leading columns dominate the distances).  The result depends on neither. */
+ * the partial-distance early exit effective.  prefix_test selects the search strategy: 0 plain
+ * float64 filter, 1 early exit on the two leading columns (raw features), 2 float32 filter,
+ * 3 tensor-core candidate filter (float16 x 3 split, mma.sync) followed by exact float64
+ * selection - for centred data of moderate range (StandardScaler / PCA outputs); data that does
+ * not fit float16 is detected on the device and searched exhaustively.  The result depends on
+ * neither col_order nor prefix_test. */
 int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, int32_t k,
             const int32_t* col_order, int32_t prefix_test, int32_t* idx_dev, void* stream);
+/* Test hook for strategy 3.  Synchronises.  err_host receives the largest observed
+ * |estimate - d^2| / (|q|^2 + |x|^2 + 1e-3) of the tensor-core distance estimate over all pairs
+ * (the filter assumes 6e-5); n, nq <= 2^22, meant for small inputs. */
+int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, float* err_host,
+                     void* stream);
 /* SMOTE._make_samples: X_new[j] = C[row] + steps[j] * (C[nn[row][1 + col]] - C[row]) with
  * row = sample_idx[j] / k, col = sample_idx[j] % k; nn_dev int32 [n_min][k + 1] from f16_knn. */
 int f16_smote_generate(const double* C_dev, int64_t n_min, int32_t d, const int32_t* nn_dev, int32_t k,

@@ -13,10 +13,16 @@ for fs, pre in (("Flake16", "None"), ("Flake16", "Scaling"), ("FlakeFlagger", "S
     A = torch.from_numpy(X[:90000]).cuda()
     B = torch.cat([A, A[:88200] * 0.5 + A[1800:90000] * 0.5]).contiguous()      # 178 200 rows, SMOTE-like
     for M, name in ((A, "90k"), (B, "178k")):
-        ops.knn(M, M, 4, co); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            ops.knn(M, M, 4, co)
-        e1.record(); torch.cuda.synchronize()
-        print("%-12s %-8s mode=%d %-5s %7.2f ms" % (fs, pre, co[1], name, e0.elapsed_time(e1) / 3), flush=True)
+        ref = None
+        for mode in sorted({co[1], 0}):
+            cm = (co[0], mode)
+            out = ops.knn(M, M, 4, cm); torch.cuda.synchronize()
+            if ref is None:
+                ref = out
+            same = bool(torch.equal(out, ref))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ops.knn(M, M, 4, cm)
+            e1.record(); torch.cuda.synchronize()
+            print("%-12s %-8s mode=%d %-5s %7.2f ms  same=%s" % (fs, pre, mode, name, e0.elapsed_time(e1) / 3, same), flush=True)
