@@ -55,8 +55,27 @@ struct TcPerm { int c[F16_MAX_D]; };
 // hi / lo: [n][16] halfs (zero padded), nrm: [n] float.  A coordinate that does not fit float16
 // (or is not finite) raises *bad: the filter is skipped and every query is searched exhaustively
 // in float64 - slow, but the result never depends on the filter being applicable.
-__global__ void k_knn_tc_prep(const double* __restrict__ A, int n, int d, __half* __restrict__ hi, __half* __restrict__ lo,
-                              float* __restrict__ nrm, int* __restrict__ bad) {
+// Euclidean distances are translation invariant: both point sets are shifted by the reference
+// set's column means (colsum / n) first, which minimises the norms the filter's error band is
+// relative to (uncentred raw columns would make the band wider than the neighbour distances).
+__global__ void k_knn_tc_colsum(const double* __restrict__ A, int n, int d, double* __restrict__ colsum) {
+    __shared__ double s_sum[F16_MAX_D];
+    if (threadIdx.x < F16_MAX_D) s_sum[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int c = threadIdx.x % F16_MAX_D;               // blockDim is a multiple of 16
+    double acc = 0.0;
+    if (c < d) {
+        for (size_t i = (size_t)blockIdx.x * (blockDim.x / F16_MAX_D) + threadIdx.x / F16_MAX_D; i < (size_t)n;
+             i += (size_t)gridDim.x * (blockDim.x / F16_MAX_D))
+            acc += A[i * d + c];
+        atomicAdd(&s_sum[c], acc);
+    }
+    __syncthreads();
+    if (threadIdx.x < d) atomicAdd(&colsum[threadIdx.x], s_sum[threadIdx.x]);
+}
+
+__global__ void k_knn_tc_prep(const double* __restrict__ A, int n, int d, const double* __restrict__ colsum, double inv_n,
+                              __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ nrm, int* __restrict__ bad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = 0.0;
@@ -64,7 +83,7 @@ __global__ void k_knn_tc_prep(const double* __restrict__ A, int n, int d, __half
     __half h[16], l[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) {
-        double v = (c < d) ? A[(size_t)i * d + c] : 0.0;
+        double v = (c < d) ? A[(size_t)i * d + c] - colsum[c] * inv_n : 0.0;
         if (!(fabs(v) <= TC_MAXABS)) ok = false;
         __half hv = __double2half(v);
         h[c] = hv;
@@ -103,7 +122,8 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
                                                           const float* __restrict__ Qn, int nq,
                                                           uint32_t* __restrict__ cand, int* __restrict__ cand_cnt,
                                                           const double* __restrict__ A64, const double* __restrict__ Q64, int d,
-                                                          float* __restrict__ probe_out) {
+                                                          float* __restrict__ probe_out, const double* __restrict__ colsum,
+                                                          double inv_n) {
     __shared__ __align__(16) __half s_hi[2][TC_TILE * TC_RS];
     __shared__ __align__(16) __half s_lo[2][TC_TILE * TC_RS];
     __shared__ __align__(16) float s_nr[2][TC_TILE];
@@ -211,7 +231,8 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
                         if (qrow[r] < nq && j < n) {
                             double s = 0.0, na = 0.0, nb = 0.0;
                             for (int c = 0; c < d; c++) {
-                                double a = Q64[(size_t)qrow[r] * d + c], b = A64[(size_t)j * d + c];
+                                const double mu = colsum[c] * inv_n;
+                                double a = Q64[(size_t)qrow[r] * d + c] - mu, b = A64[(size_t)j * d + c] - mu;
                                 s = fma(a - b, a - b, s); na = fma(a, a, na); nb = fma(b, b, nb);
                             }
                             const float nrv = (o & 1) ? nr.y : nr.x;
@@ -342,7 +363,16 @@ struct TcBuffers {
     float *an = nullptr, *qn = nullptr;
     uint32_t* cand = nullptr;
     int* cnt = nullptr;
+    double* colsum = nullptr;
 };
+
+// column sums of the reference set, then the float16 split of both sets about the column means
+static void tc_prepare(TcBuffers& b, const double* A, int n, const double* Q, int nq, int d, bool same, cudaStream_t st) {
+    k_knn_tc_colsum<<<296, 256, 0, st>>>(A, n, d, b.colsum);
+    const double inv_n = 1.0 / (double)n;
+    k_knn_tc_prep<<<(n + 127) / 128, 128, 0, st>>>(A, n, d, b.colsum, inv_n, b.ah, b.al, b.an, b.cnt + nq);
+    if (!same) k_knn_tc_prep<<<(nq + 127) / 128, 128, 0, st>>>(Q, nq, d, b.colsum, inv_n, b.qh, b.ql, b.qn, b.cnt + nq);
+}
 
 static int tc_alloc(TcBuffers& b, int n, int nq, bool same, cudaStream_t st) {
     CUDA_TRY(f16_malloc_async((void**)&b.ah, sizeof(__half) * 16 * (size_t)n, st));
@@ -356,11 +386,13 @@ static int tc_alloc(TcBuffers& b, int n, int nq, bool same, cudaStream_t st) {
     CUDA_TRY(f16_malloc_async((void**)&b.cand, sizeof(uint32_t) * TC_CAP * (size_t)nq, st));
     CUDA_TRY(f16_malloc_async((void**)&b.cnt, sizeof(int) * ((size_t)nq + 1), st));     // [nq] = 'bad data' flag
     CUDA_TRY(cudaMemsetAsync(b.cnt + nq, 0, sizeof(int), st));
+    CUDA_TRY(f16_malloc_async((void**)&b.colsum, sizeof(double) * F16_MAX_D, st));
+    CUDA_TRY(cudaMemsetAsync(b.colsum, 0, sizeof(double) * F16_MAX_D, st));
     return F16_OK;
 }
 
 static void tc_free(TcBuffers& b, cudaStream_t st) {
-    void* p[] = {b.ah, b.al, b.an, b.qh, b.ql, b.qn, b.cand, b.cnt};
+    void* p[] = {b.ah, b.al, b.an, b.qh, b.ql, b.qn, b.cand, b.cnt, b.colsum};
     for (void* x : p) if (x) cudaFreeAsync(x, st);
 }
 
@@ -373,8 +405,7 @@ int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, in
     TcBuffers b;
     int rc = tc_alloc(b, n, nq, same, st);
     if (rc != F16_OK) { tc_free(b, st); return rc; }
-    k_knn_tc_prep<<<(n + 127) / 128, 128, 0, st>>>(A, n, d, b.ah, b.al, b.an, b.cnt + nq);
-    if (!same) k_knn_tc_prep<<<(nq + 127) / 128, 128, 0, st>>>(Q, nq, d, b.qh, b.ql, b.qn, b.cnt + nq);
+    tc_prepare(b, A, n, Q, nq, d, same, st);
     const __half* qh = same ? b.ah : b.qh;
     const __half* ql = same ? b.al : b.ql;
     const float* qn = same ? b.an : b.qn;
@@ -385,12 +416,12 @@ int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, in
 #define TC_LAUNCH(KK)                                                                                            \
     case KK:                                                                                                     \
         k_knn_tc_filter<KK, false><<<grid, TC_QPB, 0, st>>>(b.ah, b.al, b.an, n, qh, ql, qn, nq, b.cand, b.cnt,   \
-                                                            nullptr, nullptr, d, nullptr);                       \
+                                                            nullptr, nullptr, d, nullptr, nullptr, 0.0);         \
         k_knn_tc_select<KK><<<sgrid, 256, 0, st>>>(A, n, Q, nq, d, pm, b.cand, b.cnt, out);                       \
         break;
     switch (k) { TC_LAUNCH(1) TC_LAUNCH(2) TC_LAUNCH(3) TC_LAUNCH(4) TC_LAUNCH(5) TC_LAUNCH(6) TC_LAUNCH(7) TC_LAUNCH(8) }
 #undef TC_LAUNCH
-    f16_count_launch(same ? 3 : 4);
+    f16_count_launch(same ? 4 : 5);
     cudaError_t e = cudaGetLastError();
     tc_free(b, st);
     if (e != cudaSuccess) { f16_set_error("f16_knn (tensor filter): %s", cudaGetErrorString(e)); return F16_ERR_CUDA; }
@@ -411,10 +442,10 @@ extern "C" int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_
     float* perr = nullptr;
     CUDA_TRY(f16_malloc_async((void**)&perr, sizeof(float), st));
     CUDA_TRY(cudaMemsetAsync(perr, 0, sizeof(float), st));
-    k_knn_tc_prep<<<((int)n + 127) / 128, 128, 0, st>>>(A_dev, (int)n, d, b.ah, b.al, b.an, b.cnt + nq);
-    k_knn_tc_prep<<<((int)nq + 127) / 128, 128, 0, st>>>(Q_dev, (int)nq, d, b.qh, b.ql, b.qn, b.cnt + nq);
+    tc_prepare(b, A_dev, (int)n, Q_dev, (int)nq, d, false, st);
     k_knn_tc_filter<4, true><<<((int)nq + TC_QPB - 1) / TC_QPB, TC_QPB, 0, st>>>(b.ah, b.al, b.an, (int)n, b.qh, b.ql, b.qn, (int)nq,
-                                                                              b.cand, b.cnt, A_dev, Q_dev, d, perr);
+                                                                              b.cand, b.cnt, A_dev, Q_dev, d, perr, b.colsum,
+                                                                              1.0 / (double)n);
     CUDA_TRY(cudaMemcpyAsync(err_host, perr, sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaFreeAsync(perr, st));

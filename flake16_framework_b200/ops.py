@@ -218,6 +218,33 @@ def variance_order(X):
     return order, 0
 
 
+def calibrate_knn(X, col_order, k=4, n_queries=32768):
+    """Picks the k-NN strategy for a device matrix by MEASURING it: ``variance_order``'s static
+    choice against the plain float64 search on a strided sample of queries (all strategies return
+    the same neighbours, so this is a pure speed decision; e.g. uncentred raw columns make the
+    tensor-core filter's norm-relative band useless and its candidate lists overflow).
+    Synchronises; meant for the one-off preparation of a dataset."""
+    order, mode = col_order
+    if mode == 0 or X.shape[0] < 2 * n_queries:
+        return order, mode
+    stride = X.shape[0] // n_queries
+    Q = X[::stride][:n_queries].contiguous()
+    best, best_ms = mode, None
+    for m in (mode, 0):
+        # strategy 3 falls back to 0 below its size threshold: force it (4) so the sample tells
+        cm = (order, 4 if m == 3 else m)
+        knn(X, Q, k, cm)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        knn(X, Q, k, cm)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best_ms is None or ms < best_ms:
+            best, best_ms = m, ms
+    return order, best
+
+
 def knn_tc_probe(A, Q):
     """Largest observed relative error of the tensor-core distance estimate (test hook)."""
     L = _ready()

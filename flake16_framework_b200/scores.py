@@ -77,6 +77,12 @@ class _DeviceData:
 
     def __init__(self, gd, device):
         self.X = {k: torch.from_numpy(v).to(device) for k, v in gd.datasets.items()}
+        # k-NN strategy per dataset: the static choice, confirmed by a measurement on the device
+        self.col_order, seen = {}, {}
+        for key, co in gd.col_order.items():
+            if key[1:] not in seen:                      # the matrix depends on (feature set, preprocessing) only
+                seen[key[1:]] = ops.calibrate_knn(self.X[key], co)
+            self.col_order[key] = seen[key[1:]]
         self.y = {k: torch.from_numpy(v.astype(np.uint8)).to(device) for k, v in gd.labels.items()}
         self.proj = torch.from_numpy(gd.proj_id).to(device)
         self.fold_idx = {}
@@ -306,7 +312,7 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
                     except queue.Empty:
                         break
                     timers = []
-                    with ops.column_order(gd.col_order[u[0]]):
+                    with ops.column_order(dd.col_order[u[0]]):
                         events, keep = _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators,
                                                  timers, model_streams)
                     pending.append((events, keep, timers))
