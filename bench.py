@@ -17,6 +17,8 @@ fixed) and the counts are all-reduced once.
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")    # before any CUDA call (see flake16_framework_b200/__init__.py)
 import subprocess
 import sys
 import tempfile
@@ -37,7 +39,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-tests", type=int, default=100000)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("F16_STREAMS", "8")))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("F16_STREAMS", "4")))
     ap.add_argument("--configs", default="grid216", help="grid216 | slice (1 dataset, 18 configs; for quick checks)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -21,6 +21,8 @@ Extra, non-reference commands used by the tests / bench:
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")    # before any CUDA call (see flake16_framework_b200/__init__.py)
+
 TESTS_FILE = "tests.json"       # experiment.py:34
 SCORES_FILE = "scores.pkl"      # experiment.py:35
 
@@ -32,7 +34,7 @@ def write_scores():
         sys.stdout.write(f"{done}/{total - done}\r")
         sys.stdout.flush()
 
-    n_streams = int(os.environ.get("F16_STREAMS", "8"))
+    n_streams = int(os.environ.get("F16_STREAMS", "4"))
     _, wall = S.write_scores(TESTS_FILE, SCORES_FILE, n_streams=n_streams, progress=progress)
     if int(os.environ.get("RANK", "0")) == 0:
         sys.stdout.write(f"\n216 configs in {wall:.1f}s\n")

@@ -29,6 +29,7 @@ import time
 import numpy as np
 import torch
 
+from . import DEFAULT_LANES, DEFAULT_WORKERS
 from . import hostprep as hp
 from . import ops
 
@@ -251,7 +252,7 @@ def prepare(parsed, configs=None, device=None, n_splits=10):
     return gd, dd
 
 
-def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, device=None,
+def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFAULT_WORKERS, device=None,
              rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None):
     """Computes the scores dict for ``configs`` (default: the full 216 grid).
 
@@ -280,8 +281,8 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=8, d
     def worker():
         torch.cuda.set_device(device)
         stream = torch.cuda.Stream(device=device)
-        # several forests of one unit in flight: 3 side streams per forest model, 2 for the tree
-        n_lanes = int(os.environ.get("F16_LANES", "3"))
+        # several forests of one unit in flight: n_lanes side streams per forest model, 2 for the tree
+        n_lanes = int(os.environ.get("F16_LANES", str(DEFAULT_LANES)))
         model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
                          for m in MODELS}
         util = torch.cuda.Stream(device=device)     # status reads / frees of settled units
