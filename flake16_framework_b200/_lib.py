@@ -39,7 +39,7 @@ def _sources(tune):
         ("f16_sort.cu", "", []),
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
         ("f16_knn32.cu", "", []),
-        ("f16_knn_tc.cu", "", []),
+        ("f16_knn_tc.cu", "", ["-DTC_MT=%d" % t.get("TC_MT", 2)]),
     )
 
 

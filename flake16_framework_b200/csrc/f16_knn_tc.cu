@@ -41,13 +41,15 @@ extern "C" cudaError_t f16_malloc_async(void** p, size_t bytes, cudaStream_t st)
         }                                                                               \
     } while (0)
 
-#define TC_QPB 128        // queries per CTA: 4 warps x 32 rows (two m16 tiles per warp)
 #define TC_TILE 128       // reference points per shared-memory tile (double buffered)
 #define TC_RS 24          // halfs per shared row: 48-byte stride => conflict-free fragment loads
 #define TC_CAP 256        // candidate slots per query
 #define TC_EPS 6.0e-5f
 #define TC_SLACK 1.0e-6f
 #define TC_MAXABS 60000.0
+#ifndef TC_MT
+#define TC_MT 2           // m16 query tiles per warp (4 measured no faster: fewer resident warps)
+#endif
 
 struct TcPerm { int c[F16_MAX_D]; };
 
@@ -95,7 +97,8 @@ __global__ void k_knn_tc_prep(const double* __restrict__ A, int n, int d, const 
         hi[(size_t)i * 16 + c] = ok ? h[c] : __float2half(0.f);
         lo[(size_t)i * 16 + c] = ok ? l[c] : __float2half(0.f);
     }
-    nrm[i] = ok ? (float)s : 0.f;
+    // stored as the filter's accumulator seed: -|x|^2 (1 - eps) / 2
+    nrm[i] = ok ? -0.5f * ((float)s * (1.0f - TC_EPS)) : 0.f;
     if (!ok) atomicExch(bad, 1);
 }
 
@@ -115,33 +118,41 @@ __device__ __forceinline__ void tc_mma(float (&c)[4], const uint32_t (&a)[4], ui
 
 // PROBE: instead of filtering, record max |s~ - d^2| / (|q|^2 + |x|^2 + slack') over all pairs
 // (d^2 recomputed in float64) - the measured error the tests compare with TC_EPS.
-template <int K, bool PROBE>
-__global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restrict__ Ah, const __half* __restrict__ Al,
-                                                          const float* __restrict__ An, int n,
-                                                          const __half* __restrict__ Qh, const __half* __restrict__ Ql,
-                                                          const float* __restrict__ Qn, int nq,
-                                                          uint32_t* __restrict__ cand, int* __restrict__ cand_cnt,
-                                                          const double* __restrict__ A64, const double* __restrict__ Q64, int d,
-                                                          float* __restrict__ probe_out, const double* __restrict__ colsum,
-                                                          double inv_n) {
+
+// A warp owns MT m16 tiles of queries (MT*16 rows) and sweeps all references in n8 chunks:
+//   acc = -nr'/2                      (accumulator initialised from the reference norms)
+//   acc += lo_q.hi_x + hi_q.lo_x + hi_q.hi_x          (3 HMMA per tile)
+// so that -2 acc = nr' - 2 q.x and the filter test "lower bound <= U" is ONE compare per
+// output: acc >= thr[row] with thr = (nq' - U) / 2.  Rows that pass take the slow path
+// (candidate append, top-k of upper bounds, new threshold).
+template <int K, int MT, bool PROBE>
+__global__ void __launch_bounds__(128) k_knn_tc_filter2(const __half* __restrict__ Ah, const __half* __restrict__ Al,
+                                                        const float* __restrict__ An, int n,
+                                                        const __half* __restrict__ Qh, const __half* __restrict__ Ql,
+                                                        const float* __restrict__ Qn, int nq,
+                                                        uint32_t* __restrict__ cand, int* __restrict__ cand_cnt,
+                                                        const double* __restrict__ A64, const double* __restrict__ Q64, int d,
+                                                        float* __restrict__ probe_out, const double* __restrict__ colsum,
+                                                        double inv_n) {
+    constexpr int QPB = 64 * MT;          // queries per CTA: 4 warps x MT tiles x 16 rows
+    constexpr int R = 2 * MT;             // query rows per thread
     __shared__ __align__(16) __half s_hi[2][TC_TILE * TC_RS];
     __shared__ __align__(16) __half s_lo[2][TC_TILE * TC_RS];
-    __shared__ __align__(16) float s_nr[2][TC_TILE];
-    __shared__ int s_cnt[TC_QPB];
+    __shared__ __align__(16) float s_nh[2][TC_TILE];
+    __shared__ int s_cnt[QPB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int q_base = blockIdx.x * TC_QPB + warp * 32;
+    const int q_base = blockIdx.x * QPB + warp * (MT * 16);
 
-    s_cnt[tid] = 0;
+    for (int i = tid; i < QPB; i += 128) s_cnt[i] = 0;
     if (!PROBE && cand_cnt[nq] != 0) return;      // data outside the float16 range: no filter (uniform exit)
 
-    // A fragments (queries): rows g / g+8 of the two m16 tiles, k = 2t, 2t+1 (+8)
-    uint32_t ah[2][4], al[2][4];
-    float nqp[4], nq2[4], lim[4], ub[4];
-    float tk[4][K];
-    int qrow[4];
+    uint32_t ah[MT][4], al[MT][4];
+    float nqp[R], nq2[R], thr[R], ub[R];
+    float tk[R][K];
+    int qrow[R];
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
+    for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int r = mt * 2 + h;
@@ -150,15 +161,14 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
             const bool ok = q < nq;
             const uint32_t* ph = reinterpret_cast<const uint32_t*>(Qh + (size_t)(ok ? q : 0) * 16);
             const uint32_t* pl = reinterpret_cast<const uint32_t*>(Ql + (size_t)(ok ? q : 0) * 16);
-            ah[mt][h] = ok ? ph[t] : 0u;          // k = 2t, 2t+1
+            ah[mt][h] = ok ? ph[t] : 0u;          // row g (+8 for h = 1), k = 2t, 2t+1
             ah[mt][h + 2] = ok ? ph[t + 4] : 0u;  // k = 2t+8, 2t+9
             al[mt][h] = ok ? pl[t] : 0u;
             al[mt][h + 2] = ok ? pl[t + 4] : 0u;
-            const float a = ok ? Qn[q] : 0.f;
-            nq2[r] = a * (1.0f - TC_EPS);
+            nq2[r] = ok ? -2.f * Qn[q] : 0.f;     // |q|^2 (1 - eps)
             nqp[r] = nq2[r] - TC_SLACK;
             ub[r] = INFINITY;
-            lim[r] = ok ? INFINITY : -INFINITY;    // rows past nq never produce candidates
+            thr[r] = ok ? -INFINITY : INFINITY;   // rows past nq never produce candidates
 #pragma unroll
             for (int m = 0; m < K; m++) tk[r][m] = INFINITY;
         }
@@ -168,21 +178,20 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
     auto stage = [&](int buf, int base) {
         const int cnt = min(TC_TILE, n - base);
         if (cnt == TC_TILE) {
-            // 128 rows x (2 + 2) 16-byte pieces + 32 pieces of norms
-            for (int i = tid; i < TC_TILE * 2; i += TC_QPB) {
+            for (int i = tid; i < TC_TILE * 2; i += 128) {
                 const int row = i >> 1, piece = i & 1;
                 tc_cp_async16(&s_hi[buf][row * TC_RS + piece * 8], Ah + (size_t)(base + row) * 16 + piece * 8);
                 tc_cp_async16(&s_lo[buf][row * TC_RS + piece * 8], Al + (size_t)(base + row) * 16 + piece * 8);
             }
-            if (tid < TC_TILE / 4) tc_cp_async16(&s_nr[buf][tid * 4], An + base + tid * 4);
+            if (tid < TC_TILE / 4) tc_cp_async16(&s_nh[buf][tid * 4], An + base + tid * 4);
         } else {
-            // last, partial tile: plain loads, padding rows can never pass the filter
-            for (int i = tid; i < TC_TILE * 16; i += TC_QPB) {
+            // last, partial tile: plain loads; padding rows get -inf (never above a finite threshold)
+            for (int i = tid; i < TC_TILE * 16; i += 128) {
                 const int row = i >> 4, c = i & 15;
                 s_hi[buf][row * TC_RS + c] = (row < cnt) ? Ah[(size_t)(base + row) * 16 + c] : __float2half(0.f);
                 s_lo[buf][row * TC_RS + c] = (row < cnt) ? Al[(size_t)(base + row) * 16 + c] : __float2half(0.f);
             }
-            for (int i = tid; i < TC_TILE; i += TC_QPB) s_nr[buf][i] = (i < cnt) ? An[base + i] * (1.0f - TC_EPS) : INFINITY;
+            for (int i = tid; i < TC_TILE; i += 128) s_nh[buf][i] = (i < cnt) ? An[base + i] : -INFINITY;
         }
         tc_cp_commit();
     };
@@ -193,37 +202,27 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
         tc_cp_wait_all();
         __syncthreads();
         if (base + TC_TILE < n) stage(buf ^ 1, base + TC_TILE);
-        const bool full = (n - base) >= TC_TILE;     // full tiles hold raw norms (scaled on the fly)
-        const __half* thi = s_hi[buf];
-        const __half* tlo = s_lo[buf];
-        const float* tnr = s_nr[buf];
+        // B fragments of chunk ch: reference ch*8 + g, k = 2t, 2t+1 (+8); norms of columns 2t, 2t+1
+        const uint32_t* rh = reinterpret_cast<const uint32_t*>(s_hi[buf] + g * TC_RS) + t;
+        const uint32_t* rl = reinterpret_cast<const uint32_t*>(s_lo[buf] + g * TC_RS) + t;
+        const float2* pn = reinterpret_cast<const float2*>(s_nh[buf]) + t;
 #pragma unroll 2
-        for (int ch = 0; ch < TC_TILE / 8; ch++) {
-            // B fragments: reference ch*8 + g, k = 2t, 2t+1 (+8)
-            const uint32_t* rh = reinterpret_cast<const uint32_t*>(thi + (ch * 8 + g) * TC_RS);
-            const uint32_t* rl = reinterpret_cast<const uint32_t*>(tlo + (ch * 8 + g) * TC_RS);
-            const uint32_t bh0 = rh[t], bh1 = rh[t + 4], bl0 = rl[t], bl1 = rl[t + 4];
-            float2 nr = *reinterpret_cast<const float2*>(tnr + ch * 8 + 2 * t);
-            if (full) { nr.x *= (1.0f - TC_EPS); nr.y *= (1.0f - TC_EPS); }
-            float acc[2][4];
+        for (int ch = 0; ch < TC_TILE / 8; ch++, rh += 8 * TC_RS / 2, rl += 8 * TC_RS / 2, pn += 4) {
+            const uint32_t bh0 = rh[0], bh1 = rh[4], bl0 = rl[0], bl1 = rl[4];
+            const float2 nh = *pn;
+            float acc[MT][4];
             bool hit = false;
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+            for (int mt = 0; mt < MT; mt++) {
+                acc[mt][0] = nh.x; acc[mt][1] = nh.y; acc[mt][2] = nh.x; acc[mt][3] = nh.y;
                 tc_mma(acc[mt], al[mt], bh0, bh1);      // small terms first
                 tc_mma(acc[mt], ah[mt], bl0, bl1);
                 tc_mma(acc[mt], ah[mt], bh0, bh1);
-                // lower bound minus the query part: nr' - 2 acc  <=  U - nq'
-                acc[mt][0] = fmaf(-2.f, acc[mt][0], nr.x);
-                acc[mt][1] = fmaf(-2.f, acc[mt][1], nr.y);
-                acc[mt][2] = fmaf(-2.f, acc[mt][2], nr.x);
-                acc[mt][3] = fmaf(-2.f, acc[mt][3], nr.y);
-                hit = hit || (acc[mt][0] <= lim[mt * 2]) || (acc[mt][1] <= lim[mt * 2]) ||
-                      (acc[mt][2] <= lim[mt * 2 + 1]) || (acc[mt][3] <= lim[mt * 2 + 1]);
+                hit = hit || (fmaxf(acc[mt][0], acc[mt][1]) >= thr[mt * 2]) || (fmaxf(acc[mt][2], acc[mt][3]) >= thr[mt * 2 + 1]);
             }
             if (PROBE) {
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
+                for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
                     for (int o = 0; o < 4; o++) {
                         const int r = mt * 2 + (o >> 1);
@@ -235,13 +234,10 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
                                 double a = Q64[(size_t)qrow[r] * d + c] - mu, b = A64[(size_t)j * d + c] - mu;
                                 s = fma(a - b, a - b, s); na = fma(a, a, na); nb = fma(b, b, nb);
                             }
-                            const float nrv = (o & 1) ? nr.y : nr.x;
-                            if (isfinite(nrv) && isfinite(nq2[r])) {
-                                // undo the (1 - eps) scaling to compare the plain estimate with d^2
-                                double est = (double)acc[mt][o] - (double)nrv + (double)nrv / (1.0 - (double)TC_EPS)
-                                             + (double)nq2[r] / (1.0 - (double)TC_EPS);
-                                perr = fmaxf(perr, (float)(fabs(est - s) / (na + nb + 1e-3)));
-                            }
+                            // plain estimate |q|^2 + |x|^2 - 2 q.x: undo the (1 - eps) scaling of the norms
+                            const double nrp = -2.0 * (double)((o & 1) ? nh.y : nh.x);
+                            double est = -2.0 * (double)acc[mt][o] - nrp + (nrp + (double)nq2[r]) / (1.0 - (double)TC_EPS);
+                            perr = fmaxf(perr, (float)(fabs(est - s) / (na + nb + 1e-3)));
                         }
                     }
                 }
@@ -249,14 +245,14 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
             }
             if (__any_sync(F16_FULL, hit)) {
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
+                for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
                     for (int o = 0; o < 4; o++) {
                         const int r = mt * 2 + (o >> 1);
-                        const float l = acc[mt][o];
-                        if (l <= lim[r]) {
-                            const int j = base + ch * 8 + 2 * t + (o & 1);
-                            const float nrv = (o & 1) ? nr.y : nr.x;
+                        const int j = base + ch * 8 + 2 * t + (o & 1);
+                        if (acc[mt][o] >= thr[r] && j < n) {
+                            const float l = -2.f * acc[mt][o];                   // nr' - 2 q.x
+                            const float nrv = -2.f * ((o & 1) ? nh.y : nh.x);    // nr'
                             // upper bound of the true squared distance
                             const float u = (l + nqp[r]) + 2.2f * TC_EPS * (nrv + nq2[r]) + 4.f * TC_SLACK;
                             if (u < tk[r][K - 1]) {
@@ -266,9 +262,9 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
                                     if (tk[r][m] < tk[r][m - 1]) { float x = tk[r][m]; tk[r][m] = tk[r][m - 1]; tk[r][m - 1] = x; }
                                 }
                                 ub[r] = fminf(ub[r], tk[r][K - 1]);
-                                lim[r] = ub[r] - nqp[r];
+                                thr[r] = 0.5f * (nqp[r] - ub[r]);
                             }
-                            const int ql = warp * 32 + (r >> 1) * 16 + (r & 1) * 8 + g;
+                            const int ql = warp * (MT * 16) + (r >> 1) * 16 + (r & 1) * 8 + g;
                             const int pos = atomicAdd(&s_cnt[ql], 1);
                             if (pos < TC_CAP) cand[(size_t)qrow[r] * TC_CAP + pos] = (uint32_t)j;
                         }
@@ -279,12 +275,12 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
         // the four threads of a quad hold disjoint column subsets of the same rows: the smallest
         // of their k-th upper bounds is still an upper bound of the true k-th distance
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < R; r++) {
             float m = ub[r];
             m = fminf(m, __shfl_xor_sync(F16_FULL, m, 1));
             m = fminf(m, __shfl_xor_sync(F16_FULL, m, 2));
             ub[r] = m;
-            if (qrow[r] < nq) lim[r] = m - nqp[r];
+            if (qrow[r] < nq) thr[r] = 0.5f * (nqp[r] - m);
         }
     }
     __syncthreads();
@@ -294,8 +290,10 @@ __global__ void __launch_bounds__(TC_QPB) k_knn_tc_filter(const __half* __restri
         if (lane == 0) atomicMax(reinterpret_cast<int*>(probe_out), __float_as_int(perr));   // perr >= 0
         return;
     }
-    const int q = blockIdx.x * TC_QPB + tid;
-    if (q < nq) cand_cnt[q] = s_cnt[tid];
+    for (int i = tid; i < QPB; i += 128) {
+        const int q = blockIdx.x * QPB + i;
+        if (q < nq) cand_cnt[q] = s_cnt[i];
+    }
 }
 
 // ------------------------------------------------------------------ 3. select
@@ -411,12 +409,12 @@ int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, in
     const float* qn = same ? b.an : b.qn;
     TcPerm pm;
     for (int c = 0; c < F16_MAX_D; c++) pm.c[c] = (c < d) ? perm[c] : c;
-    const int grid = (nq + TC_QPB - 1) / TC_QPB;
+    const int grid = (nq + 64 * TC_MT - 1) / (64 * TC_MT);
     const int sgrid = (nq + 7) / 8;
 #define TC_LAUNCH(KK)                                                                                            \
     case KK:                                                                                                     \
-        k_knn_tc_filter<KK, false><<<grid, TC_QPB, 0, st>>>(b.ah, b.al, b.an, n, qh, ql, qn, nq, b.cand, b.cnt,   \
-                                                            nullptr, nullptr, d, nullptr, nullptr, 0.0);         \
+        k_knn_tc_filter2<KK, (KK <= 4 ? TC_MT : 2), false><<<(KK <= 4 ? grid : (nq + 127) / 128), 128, 0, st>>>(  \
+            b.ah, b.al, b.an, n, qh, ql, qn, nq, b.cand, b.cnt, nullptr, nullptr, d, nullptr, nullptr, 0.0);     \
         k_knn_tc_select<KK><<<sgrid, 256, 0, st>>>(A, n, Q, nq, d, pm, b.cand, b.cnt, out);                       \
         break;
     switch (k) { TC_LAUNCH(1) TC_LAUNCH(2) TC_LAUNCH(3) TC_LAUNCH(4) TC_LAUNCH(5) TC_LAUNCH(6) TC_LAUNCH(7) TC_LAUNCH(8) }
@@ -443,9 +441,8 @@ extern "C" int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_
     CUDA_TRY(f16_malloc_async((void**)&perr, sizeof(float), st));
     CUDA_TRY(cudaMemsetAsync(perr, 0, sizeof(float), st));
     tc_prepare(b, A_dev, (int)n, Q_dev, (int)nq, d, false, st);
-    k_knn_tc_filter<4, true><<<((int)nq + TC_QPB - 1) / TC_QPB, TC_QPB, 0, st>>>(b.ah, b.al, b.an, (int)n, b.qh, b.ql, b.qn, (int)nq,
-                                                                              b.cand, b.cnt, A_dev, Q_dev, d, perr, b.colsum,
-                                                                              1.0 / (double)n);
+    k_knn_tc_filter2<4, TC_MT, true><<<((int)nq + 64 * TC_MT - 1) / (64 * TC_MT), 128, 0, st>>>(
+        b.ah, b.al, b.an, (int)n, b.qh, b.ql, b.qn, (int)nq, b.cand, b.cnt, A_dev, Q_dev, d, perr, b.colsum, 1.0 / (double)n);
     CUDA_TRY(cudaMemcpyAsync(err_host, perr, sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaFreeAsync(perr, st));
