@@ -40,6 +40,7 @@ def _sources(tune):
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
         ("f16_knn32.cu", "", []),
         ("f16_knn_tc.cu", "", ["-DTC_MT=%d" % t.get("TC_MT", 2)]),
+        ("f16_knn_umma.cu", "", ["-DUM_NB=%d" % t.get("UM_NB", 2), "-DUM_STAGES=%d" % t.get("UM_STAGES", 4)]),
     )
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "f16_forest_free": ([c_void_p, c_void_p], None),
     "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p], c_int),
     "f16_knn_tc_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),
+    "f16_knn_umma_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),
     "f16_smote_generate": ([c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p], c_int),
     "f16_tomek_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),

@@ -46,6 +46,8 @@ int f16_knn32_launch(const double* A, int n, const double* Q, int nq, int d, int
                      float* c32, double* an, cudaStream_t st);
 int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
                       cudaStream_t st);
+int f16_knn_umma_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
+                        cudaStream_t st);
 
 // first-half coordinate count: even, so that halves fall on 16-byte (double2) boundaries
 template <int D> struct KnnCfg {
@@ -238,11 +240,13 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
             pm.c[c] = col_order[c];
         }
     }
-    if (prefix_test == 3 || prefix_test == 4) {     // tensor-core candidate filter + exact float64 selection (f16_knn_tc.cu)
+    if (prefix_test >= 3 && prefix_test <= 5) {     // tensor-core candidate filter + exact float64 selection
         // small problems are faster on the plain float64 kernel (three launches, candidate lists);
-        // 4 = use the filter whatever the size (parity tests)
-        if (prefix_test == 4 || (double)n * (double)nq >= 2.5e8) {
-            int r3 = f16_knn_tc_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, st);
+        // 4 / 5 = use the filter whatever the size (parity tests): 3, 4 tcgen05 + TMEM (f16_knn_umma.cu),
+        // 5 mma.sync (f16_knn_tc.cu)
+        if (prefix_test != 3 || (double)n * (double)nq >= 2.5e8) {
+            int r3 = (prefix_test == 5) ? f16_knn_tc_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, st)
+                                        : f16_knn_umma_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, st);
             if (r3 == F16_OK) return F16_OK;
             if (r3 != F16_ERR_INVALID) return r3;
         }

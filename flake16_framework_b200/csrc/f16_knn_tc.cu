@@ -426,6 +426,28 @@ int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, in
     return F16_OK;
 }
 
+// ---- pieces shared with the tcgen05 variant of the filter (f16_knn_umma.cu)
+int f16_knn_tc_cap() { return TC_CAP; }
+
+void f16_knn_tc_colsum_launch(const double* A, int n, int d, double* colsum, cudaStream_t st) {
+    k_knn_tc_colsum<<<296, 256, 0, st>>>(A, n, d, colsum);
+}
+
+// cand: [nq][TC_CAP] candidate indices, cnt: [nq + 1] counts (> TC_CAP = overflow), cnt[nq] = 'bad data'
+int f16_knn_tc_select_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm,
+                             const uint32_t* cand, const int* cnt, int32_t* out, cudaStream_t st) {
+    TcPerm pm;
+    for (int c = 0; c < F16_MAX_D; c++) pm.c[c] = (c < d) ? perm[c] : c;
+    const int sgrid = (nq + 7) / 8;
+#define TC_SELECT(KK) case KK: k_knn_tc_select<KK><<<sgrid, 256, 0, st>>>(A, n, Q, nq, d, pm, cand, cnt, out); break;
+    switch (k) {
+        TC_SELECT(1) TC_SELECT(2) TC_SELECT(3) TC_SELECT(4) TC_SELECT(5) TC_SELECT(6) TC_SELECT(7) TC_SELECT(8)
+        default: return F16_ERR_INVALID;
+    }
+#undef TC_SELECT
+    return F16_OK;
+}
+
 // Test hook: largest observed |s~ - d^2| / (|q|^2 + |x|^2 + 1e-3) of the tensor-core estimate over
 // all (query, reference) pairs (float64 recomputation on the device; small inputs only).
 extern "C" int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, float* err_host,

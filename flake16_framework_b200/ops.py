@@ -245,11 +245,12 @@ def calibrate_knn(X, col_order, k=4, n_queries=32768):
     return order, best
 
 
-def knn_tc_probe(A, Q):
-    """Largest observed relative error of the tensor-core distance estimate (test hook)."""
+def knn_tc_probe(A, Q, umma=False):
+    """Largest observed relative error of the tensor-core distance estimate (test hook);
+    ``umma`` selects the tcgen05 / TMEM implementation instead of the mma.sync one."""
     L = _ready()
     err = ctypes.c_float(0.0)
-    check(L.f16_knn_tc_probe(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], ctypes.byref(err), _stream()))
+    check((L.f16_knn_umma_probe if umma else L.f16_knn_tc_probe)(_ptr(A), A.shape[0], _ptr(Q), Q.shape[0], A.shape[1], ctypes.byref(err), _stream()))
     return float(err.value)
 
 

@@ -109,6 +109,10 @@ int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int
  * (the filter assumes 6e-5); n, nq <= 2^22, meant for small inputs. */
 int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, float* err_host,
                      void* stream);
+/* Same hook for the tcgen05 / TMEM implementation of the filter (strategy 3 uses it; strategy 5
+ * forces the mma.sync implementation, strategy 4 forces the tcgen05 one whatever the size). */
+int f16_knn_umma_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, float* err_host,
+                       void* stream);
 /* SMOTE._make_samples: X_new[j] = C[row] + steps[j] * (C[nn[row][1 + col]] - C[row]) with
  * row = sample_idx[j] / k, col = sample_idx[j] % k; nn_dev int32 [n_min][k + 1] from f16_knn. */
 int f16_smote_generate(const double* C_dev, int64_t n_min, int32_t d, const int32_t* nn_dev, int32_t k,

@@ -63,9 +63,9 @@ def test_knn_matches_sklearn(cuda, cfg):
         assert frac == 1.0, "k=%d: %.6f of rows have identical neighbour lists" % (k, frac)
         # column order / prefix early exit are pure scheduling: same result
         order, prefix = ops.variance_order(X)
-        # (4 = tensor-core filter whatever the size; raw features do not fit float16 and take its
-        #  exhaustive float64 path)
-        for co in ((order, prefix), (order, 1), (order, 2), (order, 4), (order[::-1].copy(), 0)):
+        # (4 / 5 = tensor-core filter whatever the size, tcgen05 / mma.sync implementation; raw
+        #  features do not fit float16 and take the exhaustive float64 path)
+        for co in ((order, prefix), (order, 1), (order, 2), (order, 4), (order, 5), (order[::-1].copy(), 0)):
             assert np.array_equal(ops.knn(Xd, Xd, k, co).cpu().numpy(), ours), (k, co[1])
 
 
@@ -82,9 +82,10 @@ def _smote_like(rs, n_seed, n_new, d, scale=1.0):
     return np.ascontiguousarray(X)
 
 
+@pytest.mark.parametrize("impl", [4, 5])          # 4: tcgen05 + TMEM (f16_knn_umma.cu), 5: mma.sync (f16_knn_tc.cu)
 @pytest.mark.parametrize("d", [16, 7, 3])
-def test_knn_tensor_filter_equals_float64_search(cuda, d):
-    """Strategy 3/4 (f16_knn_tc.cu) must return exactly what the float64 kernel returns."""
+def test_knn_tensor_filter_equals_float64_search(cuda, d, impl):
+    """Both tensor-core filters must return exactly what the float64 kernel returns."""
     from flake16_framework_b200 import ops
     rs = np.random.RandomState(d)
     X = _smote_like(rs, 1500, 9000, d)                       # 10 600 rows: not a multiple of 128
@@ -93,19 +94,20 @@ def test_knn_tensor_filter_equals_float64_search(cuda, d):
     order = np.arange(d, dtype=np.int32)
     for k in (1, 2, 4, 6, 8):
         ref = ops.knn(Xd, Xd, k, (order, 0)).cpu().numpy()
-        got = ops.knn(Xd, Xd, k, (order, 4)).cpu().numpy()
+        got = ops.knn(Xd, Xd, k, (order, impl)).cpu().numpy()
         assert np.array_equal(got, ref), "self-join k=%d: %d rows differ" % (k, (got != ref).any(axis=1).sum())
         refq = ops.knn(Xd, Q, k, (order, 0)).cpu().numpy()
-        gotq = ops.knn(Xd, Q, k, (order, 4)).cpu().numpy()
+        gotq = ops.knn(Xd, Q, k, (order, impl)).cpu().numpy()
         assert np.array_equal(gotq, refq), "A != Q k=%d" % k
     # tiny and huge (but float16-representable) magnitudes
     for scale in (1e-4, 300.0):
         Y = _smote_like(rs, 300, 1500, d, scale)
         Yd = torch.from_numpy(Y).cuda()
-        assert np.array_equal(ops.knn(Yd, Yd, 4, (order, 4)).cpu().numpy(), ops.knn(Yd, Yd, 4, (order, 0)).cpu().numpy()), scale
+        assert np.array_equal(ops.knn(Yd, Yd, 4, (order, impl)).cpu().numpy(), ops.knn(Yd, Yd, 4, (order, 0)).cpu().numpy()), scale
 
 
-def test_knn_tensor_filter_overflow_and_range_fallbacks(cuda):
+@pytest.mark.parametrize("impl", [4, 5])
+def test_knn_tensor_filter_overflow_and_range_fallbacks(cuda, impl):
     from flake16_framework_b200 import ops
     d = 16
     order = np.arange(d, dtype=np.int32)
@@ -115,15 +117,16 @@ def test_knn_tensor_filter_overflow_and_range_fallbacks(cuda):
     R = np.zeros((n, d)); R[:, 0] = 50.0 - 0.01 * np.arange(n); R[:, 1] = 1e-3 * np.arange(n)
     Qs = np.zeros((300, d)); Qs[:, 2] = 1e-2 * np.arange(300)
     Rd, Qd = torch.from_numpy(R).cuda(), torch.from_numpy(Qs).cuda()
-    assert np.array_equal(ops.knn(Rd, Qd, 4, (order, 4)).cpu().numpy(), ops.knn(Rd, Qd, 4, (order, 0)).cpu().numpy())
+    assert np.array_equal(ops.knn(Rd, Qd, 4, (order, impl)).cpu().numpy(), ops.knn(Rd, Qd, 4, (order, 0)).cpu().numpy())
     # one coordinate outside the float16 range: device-side detection, exhaustive search
     rs = np.random.RandomState(3)
     X = rs.randn(2000, d); X[17, 5] = 1.0e6
     Xd = torch.from_numpy(X).cuda()
-    assert np.array_equal(ops.knn(Xd, Xd, 4, (order, 4)).cpu().numpy(), ops.knn(Xd, Xd, 4, (order, 0)).cpu().numpy())
+    assert np.array_equal(ops.knn(Xd, Xd, 4, (order, impl)).cpu().numpy(), ops.knn(Xd, Xd, 4, (order, 0)).cpu().numpy())
 
 
-def test_knn_tensor_filter_error_bound(cuda):
+@pytest.mark.parametrize("umma", [True, False])
+def test_knn_tensor_filter_error_bound(cuda, umma):
     """The filter assumes |estimate - d^2| <= 6e-5 (|q|^2 + |x|^2) + slack; measured on the device
     it must stay below a quarter of that on every kind of data the grid produces."""
     from flake16_framework_b200 import ops
@@ -133,10 +136,11 @@ def test_knn_tensor_filter_error_bound(cuda):
                 dict(n=1500, fset="FlakeFlagger", prep="Scaling")):
         X, _, _ = make_dataset(**cfg)
         Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
-        worst = max(worst, ops.knn_tc_probe(Xd, Xd))
-    for scale in (1e-3, 1.0, 200.0):
+        worst = max(worst, ops.knn_tc_probe(Xd, Xd, umma))
+    # (the tcgen05 filter carries the norm seed in three float16: |x|^2 up to 2.6e8)
+    for scale in (1e-3, 1.0, 20.0 if umma else 200.0):
         Y = torch.from_numpy(_smote_like(rs, 300, 900, 16, scale)).cuda()
-        worst = max(worst, ops.knn_tc_probe(Y, Y))
+        worst = max(worst, ops.knn_tc_probe(Y, Y, umma))
     assert worst < 1.5e-5, worst
 
 

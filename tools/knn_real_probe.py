@@ -20,7 +20,7 @@ for fs in ("Flake16", "FlakeFlagger"):
         for M, name in ((Xtr, "train"), (np.ascontiguousarray(Xs), "smote")):
             Md = torch.from_numpy(M).cuda()
             ref = None
-            for mode in sorted({co[1], 0}):
+            for mode in sorted({co[1], 0} | ({5} if co[1] == 3 else set())):      # 5 = mma.sync filter
                 cm = (co[0], mode)
                 out = ops.knn(Md, Md, 4, cm); torch.cuda.synchronize()
                 if ref is None:
