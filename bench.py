@@ -200,6 +200,47 @@ def roofline_probe(parsed, L):
             "algorithmic_bytes_per_launch": alg, "kernel_ms": avg_ms, "traffic": traffic}
 
 
+def knn_roofline_probe(parsed):
+    """Second kernel reported against a roofline: the tensor-core k-NN filter (tcgen05 + TMEM).
+    Algorithmic flops = 3 d n_query n_ref; duration = CUDA events around the whole
+    f16_knn call (centring, float16 split, filter, exact float64 selection) on one standardised
+    90 000 x 16 fold; peak = measured dense bf16 tensor throughput."""
+    import numpy as np
+    import torch
+    from flake16_framework_b200 import hostprep as hp, ops
+    X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY, hp.FEATURE_SETS["Flake16"])
+    X = np.ascontiguousarray(hp.preprocess(X, "Scaling"))
+    tr, _ = next(iter(hp.kfold_split(hp.stratified_kfold_test_folds(y))))
+    A = torch.from_numpy(np.ascontiguousarray(X[tr])).cuda()
+    order, _ = ops.variance_order(X)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ms = []
+    for it in range(4):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.knn(A, A, 4, (order, 3))
+        e1.record()
+        e1.synchronize()
+        if it > 0:
+            ms.append(e0.elapsed_time(e1))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops", 1800.0))
+    n = A.shape[0]
+    flops = 3.0 * 16 * n * n
+    avg_ms = sum(ms) / len(ms)
+    achieved = flops / (avg_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "f16_knn strategy 3: k_knn_umma_filter (tcgen05) + exact float64 select, %d x %d x 16" % (n, n),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (measured)" if peaks else "fallback 1800 TFLOP/s",
+            "algorithmic_flops_per_call": flops, "call_ms": avg_ms, "traffic": None,
+            "note": "the filter is bound by its per-element epilogue (one compare per distance), not by the MMA rate"}
+
+
 def ours_arm(args):
     import numpy as np
     import torch
@@ -298,6 +339,7 @@ def ours_arm(args):
             "trees_per_s": (n_cfg // 3) * 10 * 201 * args.steps / (total_ms * 1e-3) if args.configs == "grid216" else None}
     if world == 1:
         line["roofline"] = roofline_probe(parsed, L)
+        line["roofline_knn"] = knn_roofline_probe(parsed)
         if not args.no_cpu_baseline:
             tasks, desc, workers = cpu_sample(tests_file, 1)
             v, dt = run_cpu_sample(tests_file, tasks, workers)
