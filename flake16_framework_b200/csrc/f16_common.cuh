@@ -48,6 +48,20 @@ __host__ __device__ __forceinline__ uint32_t f16_rand_r(uint32_t* s) {
 __host__ __device__ __forceinline__ int f16_rand_int(int lo, int hi, uint32_t* s) {
     return lo + (int)(f16_rand_r(s) % (uint32_t)(hi - lo));
 }
+#ifdef __CUDACC__
+// rand_int for ranges up to 16 (the feature draws, d <= 16): r % m by one multiply-high with
+// floor(2^32 / m) and a single correction - the estimate is never more than one below r / m
+// (r < 2^32), so the result equals the `%` above for every r.
+static __constant__ uint32_t f16_magic16[17] = {0x00000000u, 0xffffffffu, 0x80000000u, 0x55555555u, 0x40000000u, 0x33333333u, 0x2aaaaaaau, 0x24924924u, 0x20000000u, 0x1c71c71cu, 0x19999999u, 0x1745d174u, 0x15555555u, 0x13b13b13u, 0x12492492u, 0x11111111u, 0x10000000u};
+__device__ __forceinline__ int f16_rand_int_small(int lo, int hi, uint32_t* s) {
+    const uint32_t r = f16_rand_r(s);
+    const uint32_t m = (uint32_t)(hi - lo);                       // 1 .. 16
+    const uint32_t magic = f16_magic16[m];                        // min(2^32 - 1, floor(2^32 / m))
+    uint32_t rem = r - __umulhi(r, magic) * m;
+    if (rem >= m) rem -= m;
+    return lo + (int)rem;
+}
+#endif
 // ((high - low) * r / RAND_R_MAX) + low, float64, this exact operation order, no FMA.
 __device__ __forceinline__ double f16_rand_uniform(double lo, double hi, uint32_t* s) {
     double r = (double)f16_rand_r(s);

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     c.best_f = s_eval_f[k];
                     c.best_thr = (double)best.v_prev / 2.0 + (double)best.v / 2.0;
                     c.n_left = p; c.l0 = best.l0; c.l1 = best.l1;
-                    c.split = improvement_ok(best.l0, best.l1, t0, t1, W_total) ? 1 : 0;
+                    c.split = (improvement_certain(t0, t1, n) || improvement_ok(best.l0, best.l1, t0, t1, W_total)) ? 1 : 0;
                 }
                 __syncthreads();
                 PH_T(1, sm ? 6 : 3);

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                         int nl = (int)(uint32_t)s_cnt[bk], l1 = (int)(s_cnt[bk] >> 32), l0 = nl - l1;
                         c.best_f = s_cand_f[bk]; c.best_thr = s_cand_thr[bk]; c.node_id_k = bk;
                         c.n_left = nl; c.l0 = l0; c.l1 = l1;
-                        c.split = improvement_ok(l0, l1, c.c0, c.c1, W_total) ? 1 : 0;
+                        c.split = (improvement_certain(c.c0, c.c1, n) || improvement_ok(l0, l1, c.c0, c.c1, W_total)) ? 1 : 0;
                     }
                 }
             }

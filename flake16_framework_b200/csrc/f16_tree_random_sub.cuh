@@ -24,6 +24,19 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
     uint32_t rng = ds.rng;
     const int d = P.d, max_features = P.max_features;
     const int mf = lane % DP, mg = lane / DP;
+    // The splitter's Fisher-Yates permutation and its constant-feature list (16 entries of 4 bits
+    // each) live in two registers for the whole subtree - every lane holds the same words - so a
+    // feature draw is pure ALU work: no shared-memory round trip, no __syncwarp per swap.
+    auto perm_get = [](unsigned long long w, int i) -> uint32_t { return (uint32_t)(w >> (4 * i)) & 15u; };
+    auto perm_set = [](unsigned long long w, int i, uint32_t v) -> unsigned long long {
+        return (w & ~(15ull << (4 * i))) | ((unsigned long long)v << (4 * i));
+    };
+    unsigned long long F = 0, C = 0;
+#pragma unroll
+    for (int i = 0; i < F16_MAX_D; i++) {
+        F |= (unsigned long long)(ds.features[i] & 15) << (4 * i);
+        C |= (unsigned long long)(ds.const_feats[i] & 15) << (4 * i);
+    }
 
     while (sp > 0) {
         F16StackRec r = stk.get(sp - 1);
@@ -119,32 +132,26 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
 
             while (f_i > n_total && (n_visited < max_features || n_visited <= n_found + n_drawn)) {
                 n_visited++;
-                int f_j = f16_rand_int(n_drawn, f_i - n_found, &rng);
+                int f_j = f16_rand_int_small(n_drawn, f_i - n_found, &rng);
                 if (f_j < n_known) {
-                    int a = ds.features[n_drawn], b = ds.features[f_j];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[n_drawn] = b; ds.features[f_j] = a; }
-                    __syncwarp();
+                    const uint32_t a = perm_get(F, n_drawn), b = perm_get(F, f_j);
+                    F = perm_set(perm_set(F, n_drawn, b), f_j, a);
                     n_drawn++;
                     continue;
                 }
                 f_j += n_found;
-                const int f = ds.features[f_j];
+                const int f = (int)perm_get(F, f_j);
                 const float fmn = __shfl_sync(F16_FULL, mn, f), fmx = __shfl_sync(F16_FULL, mx, f);
                 if (fmx <= __fadd_rn(fmn, 1e-7f)) {
-                    int b = ds.features[n_total];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[f_j] = b; ds.features[n_total] = f; }
-                    __syncwarp();
+                    const uint32_t b = perm_get(F, n_total);
+                    F = perm_set(perm_set(F, f_j, b), n_total, (uint32_t)f);
                     n_found++; n_total++;
                     continue;
                 }
                 f_i--;
                 {
-                    int b = ds.features[f_i];
-                    __syncwarp();
-                    if (lane == 0) { ds.features[f_i] = f; ds.features[f_j] = b; }
-                    __syncwarp();
+                    const uint32_t b = perm_get(F, f_i);
+                    F = perm_set(perm_set(F, f_i, (uint32_t)f), f_j, b);
                 }
                 // the draw consumes the generator now; the float64 division of rand_uniform is
                 // deferred so that the (up to 4) thresholds of a chunk are divided on 4 lanes at once
@@ -155,16 +162,24 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
                 if (ncand == 4) { finish_thresholds(); eval_chunk(4); ncand = 0; }
             }
             if (ncand > 0) { finish_thresholds(); eval_chunk(ncand); }
-            __syncwarp();
-            if (lane == 0) {
-                for (int i = 0; i < n_known; i++) ds.features[i] = ds.const_feats[i];
-                for (int i = n_known; i < n_total; i++) ds.const_feats[i] = ds.features[i];
+            // features[0 : n_known] = const_feats[0 : n_known];  const_feats[n_known : n_total] =
+            // features[n_known : n_total]   (sklearn/tree/_splitter.pyx:473-478), on the packed words
+            {
+                const unsigned long long lowm = (n_known >= 16) ? ~0ull : ((1ull << (4 * n_known)) - 1ull);
+                const unsigned long long uppm = (n_total >= 16) ? ~0ull : ((1ull << (4 * n_total)) - 1ull);
+                F = (F & ~lowm) | (C & lowm);
+                C = (C & ~(uppm & ~lowm)) | (F & (uppm & ~lowm));
             }
-            __syncwarp();
-            for (int i = n_known; i < n_total; i++) cmask |= 1u << ds.const_feats[i];
+            for (int i = n_known; i < n_total; i++) cmask |= 1u << perm_get(C, i);
 
-            // ---- (c) improvement test: lane 0 parent term, lane 1 right term, lane 2 left term
-            if (best_f >= 0) {
+            // ---- (c) improvement test: lane 0 parent term, lane 1 right term, lane 2 left term.
+            //      For a node holding at most 1/16 of the training weight the test cannot fail: the
+            //      computed (imp - B - C) is its non-negative true value minus at most 8 roundings of
+            //      quantities <= 1 (> -9e-16), scaled by w_node / W <= 1/16 that is > -6e-17, four
+            //      times smaller than EPSILON - so the three divisions are skipped.
+            if (best_f >= 0 && improvement_certain(t0, t1, P.n)) {
+                split = true;
+            } else if (best_f >= 0) {
                 const int role = lane % 3;
                 double a, b, num, den;
                 const double wn = (double)t0 + (double)t1;
@@ -224,5 +239,9 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, con
         }
         __syncwarp();
     }
-    if (lane == 0) { c.sp = sp; c.node_count = node_count; ds.rng = rng; }
+    if (lane == 0) {
+        c.sp = sp; c.node_count = node_count; ds.rng = rng;
+#pragma unroll
+        for (int i = 0; i < F16_MAX_D; i++) { ds.features[i] = (int)perm_get(F, i); ds.const_feats[i] = (int)perm_get(C, i); }
+    }
 }
