@@ -4,13 +4,16 @@
 stage (reference experiment.py:693-714 dispatches setup|container|run|tests|scores|shap|figures).
 
     python experiment.py scores        # reads ./tests.json, writes ./scores.pkl
+    python experiment.py tests         # reads ./data/, writes ./tests.json (the step before; host only)
 
 ``scores`` keeps the reference's file names (experiment.py:34-35) and pickle schema
 (experiment.py:488-490,498-501) but runs on B200 GPUs through libf16_b200.so.  Under
 ``torchrun`` (WORLD_SIZE > 1) the (dataset, fold) units are sharded over one process per GPU
 and the integer counts are all-reduced over NCCL; rank 0 writes the pickle.
 
-The other reference commands (data collection in Docker, collation, SHAP, LaTeX figures) are
+``tests`` is the collation step that produces the hot path's input; it is
+host-side bookkeeping with the reference's function names (flake16_framework_b200/collate.py).
+The other reference commands (data collection in Docker, SHAP, LaTeX figures) are
 outside this repo's scope and raise the same ``ValueError`` the
 reference raises for an unrecognised command (experiment.py:712-714).
 
@@ -40,16 +43,26 @@ def write_scores():
         sys.stdout.write(f"\n216 configs in {wall:.1f}s\n")
 
 
-if __name__ == "__main__":
-    if len(sys.argv) > 1:
-        command, *args = sys.argv[1:]
+def write_tests():
+    """`tests`: raw run data under ./data -> ./tests.json (reference experiment.py:376-407)."""
+    from flake16_framework_b200 import collate
+    collate.write_tests(collate.DATA_DIR, TESTS_FILE)
 
-        if command == "scores" and not args:
-            write_scores()
-        elif command == "synth" and args:
-            from flake16_framework_b200 import synth
-            synth.make_tests_json(TESTS_FILE, int(args[0]), int(args[1]) if len(args) > 1 else 16)
-        else:
-            raise ValueError("Unrecognized command given.")
-    else:
+
+def main(argv):
+    if not argv:
         raise ValueError("No command given.")
+    command, *args = argv
+    if command == "scores" and not args:
+        write_scores()
+    elif command == "tests" and not args:
+        write_tests()
+    elif command == "synth" and args:
+        from flake16_framework_b200 import synth
+        synth.make_tests_json(TESTS_FILE, int(args[0]), int(args[1]) if len(args) > 1 else 16)
+    else:
+        raise ValueError("Unrecognized command given.")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
