@@ -40,6 +40,7 @@ def _sources(tune):
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
         ("f16_knn32.cu", "", []),
         ("f16_knn_tc.cu", "", ["-DTC_MT=%d" % t.get("TC_MT", 2)]),
+        ("f16_knn_sweep.cu", "", []),
         ("f16_knn_umma.cu", "", ["-DUM_NB=%d" % t.get("UM_NB", 2), "-DUM_STAGES=%d" % t.get("UM_STAGES", 4)]),
     )
 

@@ -48,6 +48,8 @@ int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, in
                       cudaStream_t st);
 int f16_knn_umma_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
                         cudaStream_t st);
+int f16_knn_sweep_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
+                         cudaStream_t st);
 
 // first-half coordinate count: even, so that halves fall on 16-byte (double2) boundaries
 template <int D> struct KnnCfg {
@@ -239,6 +241,12 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
             seen |= 1u << col_order[c];
             pm.c[c] = col_order[c];
         }
+    }
+    if (prefix_test == 6) {     // sweep over the rows sorted by the leading (dominant) column (f16_knn_sweep.cu)
+        int r6 = f16_knn_sweep_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, st);
+        if (r6 == F16_OK) return F16_OK;
+        if (r6 != F16_ERR_INVALID) return r6;
+        prefix_test = 1;
     }
     if (prefix_test >= 3 && prefix_test <= 5) {     // tensor-core candidate filter + exact float64 selection
         // small problems are faster on the plain float64 kernel (three launches, candidate lists);

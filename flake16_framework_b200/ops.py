@@ -230,7 +230,7 @@ def calibrate_knn(X, col_order, k=4, n_queries=32768):
     stride = X.shape[0] // n_queries
     Q = X[::stride][:n_queries].contiguous()
     best, best_ms = mode, None
-    for m in (mode, 0):
+    for m in ((mode, 6, 0) if mode == 1 else (mode, 0)):      # 6 = sorted sweep, only where one column dominates
         # strategy 3 falls back to 0 below its size threshold: force it (4) so the sample tells
         cm = (order, 4 if m == 3 else m)
         knn(X, Q, k, cm)

@@ -100,8 +100,10 @@ void f16_forest_free(f16_forest* forest, void* stream);
  * float64 filter, 1 early exit on the two leading columns (raw features), 2 float32 filter,
  * 3 tensor-core candidate filter (float16 x 3 split, mma.sync) followed by exact float64
  * selection - for centred data of moderate range (StandardScaler / PCA outputs); data that does
- * not fit float16 is detected on the device and searched exhaustively.  The result depends on
- * neither col_order nor prefix_test. */
+ * not fit float16 is detected on the device and searched exhaustively; 6 sweep over the rows sorted
+ * by the leading column of col_order, outwards from the query until the gap in that column alone
+ * exceeds the k-th best distance - for raw data whose variance sits in one column.  The result
+ * depends on neither col_order nor prefix_test. */
 int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, int32_t k,
             const int32_t* col_order, int32_t prefix_test, int32_t* idx_dev, void* stream);
 /* Test hook for strategy 3.  Synchronises.  err_host receives the largest observed

@@ -65,7 +65,8 @@ def test_knn_matches_sklearn(cuda, cfg):
         order, prefix = ops.variance_order(X)
         # (4 / 5 = tensor-core filter whatever the size, tcgen05 / mma.sync implementation; raw
         #  features do not fit float16 and take the exhaustive float64 path)
-        for co in ((order, prefix), (order, 1), (order, 2), (order, 4), (order, 5), (order[::-1].copy(), 0)):
+        # (6 = sweep over the rows sorted by the leading column of the order)
+        for co in ((order, prefix), (order, 1), (order, 2), (order, 4), (order, 5), (order, 6), (order[::-1].copy(), 6), (order[::-1].copy(), 0)):
             assert np.array_equal(ops.knn(Xd, Xd, k, co).cpu().numpy(), ours), (k, co[1])
 
 
@@ -82,7 +83,7 @@ def _smote_like(rs, n_seed, n_new, d, scale=1.0):
     return np.ascontiguousarray(X)
 
 
-@pytest.mark.parametrize("impl", [4, 5])          # 4: tcgen05 + TMEM (f16_knn_umma.cu), 5: mma.sync (f16_knn_tc.cu)
+@pytest.mark.parametrize("impl", [4, 5, 6])       # 4: tcgen05 + TMEM (f16_knn_umma.cu), 5: mma.sync (f16_knn_tc.cu), 6: sorted sweep (f16_knn_sweep.cu)
 @pytest.mark.parametrize("d", [16, 7, 3])
 def test_knn_tensor_filter_equals_float64_search(cuda, d, impl):
     """Both tensor-core filters must return exactly what the float64 kernel returns."""
@@ -106,7 +107,7 @@ def test_knn_tensor_filter_equals_float64_search(cuda, d, impl):
         assert np.array_equal(ops.knn(Yd, Yd, 4, (order, impl)).cpu().numpy(), ops.knn(Yd, Yd, 4, (order, 0)).cpu().numpy()), scale
 
 
-@pytest.mark.parametrize("impl", [4, 5])
+@pytest.mark.parametrize("impl", [4, 5, 6])
 def test_knn_tensor_filter_overflow_and_range_fallbacks(cuda, impl):
     from flake16_framework_b200 import ops
     d = 16
