@@ -244,3 +244,21 @@ def test_abi_argument_validation_without_gpu():
     assert L.f16_knn(fake, 100, fake, 100, 16, 4, bad_order, 0, fake, None) == -1                       # not a permutation
     assert L.f16_confusion(fake, fake, fake, 10, 0, fake, None) == -1
     assert L.f16_tree_seeds(0, 1, 0, fake, fake) == -1
+
+
+def test_small_modulus_table_in_common_header():
+    """f16_rand_int_small (f16_common.cuh) replaces `r % m` (m <= 16) by a multiply-high with
+    floor(2^32 / m) and one correction: check the committed table and the identity on the host."""
+    import re
+    src = open(os.path.join(ROOT, "flake16_framework_b200", "csrc", "f16_common.cuh")).read()
+    table = [int(x, 16) for x in re.search(r"f16_magic16\[17\] = \{([^}]*)\}", src).group(1).replace("u", "").split(",")]
+    assert len(table) == 17
+    rs = np.random.RandomState(0)
+    for m in range(1, 17):
+        assert table[m] == min(0xffffffff, (1 << 32) // m)
+        rr = np.concatenate([np.array([0, 1, m - 1, m, m + 1, 2**31 - 2, 2**31 - 1], dtype=np.uint64),
+                             rs.randint(0, 2**31, 20000).astype(np.uint64)])
+        q = (rr * np.uint64(table[m])) >> np.uint64(32)
+        rem = rr - q * np.uint64(m)
+        rem = np.where(rem >= m, rem - np.uint64(m), rem)
+        assert np.array_equal(rem, rr % np.uint64(m)), m
