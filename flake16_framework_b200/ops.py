@@ -6,6 +6,7 @@ back: a missing library or a failing call raises ``F16Error``.
 """
 
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -225,6 +226,9 @@ def calibrate_knn(X, col_order, k=4, n_queries=32768):
     tensor-core filter's norm-relative band useless and its candidate lists overflow).
     Synchronises; meant for the one-off preparation of a dataset."""
     order, mode = col_order
+    forced = os.environ.get("F16_KNN_STRATEGY")          # e.g. under a profiler, whose per-launch overhead skews the timing
+    if forced is not None:
+        return order, int(forced)
     if mode == 0 or X.shape[0] < 2 * n_queries:
         return order, mode
     stride = X.shape[0] // n_queries
