@@ -1,17 +1,19 @@
 // tcgen05 / TMEM variant of the k-NN candidate filter (see f16_knn_tc.cu for the method and its
 // error budget; the candidate lists, the exact float64 selection and the result are the same).
 //
-// One CTA owns 128 queries (UMMA M = 128) and sweeps the references in tiles of 128 (UMMA N):
+// One CTA owns NB = 2 blocks of 128 queries (UMMA M = 128) and sweeps the references in tiles of
+// 128 (UMMA N); per block and tile
 //   D[128 x 128] (TMEM, float32)  =  lo_q.hi_x + hi_q.lo_x + [2048 1 2^-11 0..].[s0 s1 s2 0..] + hi_q.hi_x
-// four tcgen05.mma.kind::f16 (K = 16) per tile, issued by one thread.  The third product adds the
+// four tcgen05.mma.kind::f16 (K = 16), issued by one thread.  The third product adds the
 // reference's accumulator seed nh = -|x|^2 (1 - eps) / 2 (split in three float16), so that a TMEM
 // lane (= query row) holds  q.x - nr'/2  and the filter test is one compare per element against
 // the row's threshold (nq' - U) / 2.
 // Warp roles: warp 0 = bulk-copy producer (cp.async.bulk + mbarrier complete_tx), warp 1 = TMEM
-// owner and MMA issuer, warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns, one query per
-// thread: the running top-k of upper bounds, the threshold and the candidate counter are plain
-// registers; no atomics).  Two TMEM accumulators (2 x 128 columns) let the MMAs of tile t+1
-// overlap the epilogue of tile t; a 4-stage shared-memory ring feeds the MMAs.
+// owner and MMA issuer, warps 2..9 = epilogue, four per query block (tcgen05.ld 32 lanes x 32
+// columns, one query per thread: the running top-k of upper bounds, the threshold and the
+// candidate counter are plain registers; no atomics).  Two TMEM accumulators per block (NB x 2 x
+// 128 = 512 columns) let the MMAs of tile t+1 overlap the epilogue of tile t; a 4-stage
+// shared-memory ring feeds the MMAs, and every reference tile is used by both query blocks.
 // Operands are stored by the prep kernel in the canonical K-major no-swizzle layout of the
 // tensor core ("core matrices" of 8 rows x 16 bytes): per 8 points 256 bytes =
 // [k 0..7 of the 8 points][k 8..15 of the 8 points], so a tile is one contiguous 4 KB block,
