@@ -1,4 +1,6 @@
-// Tensor-core candidate filter for the exact k-nearest-neighbour search (f16_knn, mode 3).
+// Tensor-core candidate filter for the exact k-nearest-neighbour search: the mma.sync version
+// (f16_knn strategy 5) and the pieces it shares with the tcgen05 version (strategy 3,
+// f16_knn_umma.cu): column sums, candidate-list format, exact float64 selection.
 //
 // The float64 search (f16_knn.cu) is bound by the FP64 pipe: n * nq * d DFMAs.  For centred,
 // moderately scaled data (StandardScaler / PCA outputs) almost all of that arithmetic only proves
@@ -118,7 +120,7 @@ __device__ __forceinline__ void tc_mma(float (&c)[4], const uint32_t (&a)[4], ui
 
 // PROBE: instead of filtering, record max |s~ - d^2| / (|q|^2 + |x|^2 + slack') over all pairs
 // (d^2 recomputed in float64) - the measured error the tests compare with TC_EPS.
-
+//
 // A warp owns MT m16 tiles of queries (MT*16 rows) and sweeps all references in n8 chunks:
 //   acc = -nr'/2                      (accumulator initialised from the reference norms)
 //   acc += lo_q.hi_x + hi_q.lo_x + hi_q.hi_x          (3 HMMA per tile)
