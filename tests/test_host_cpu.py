@@ -262,3 +262,21 @@ def test_small_modulus_table_in_common_header():
         rem = rr - q * np.uint64(m)
         rem = np.where(rem >= m, rem - np.uint64(m), rem)
         assert np.array_equal(rem, rr % np.uint64(m)), m
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_unit_plan_is_a_balanced_partition(world):
+    """(dataset, fold) units are assigned longest-processing-time-first; every rank
+    derives the same plan without communicating, every unit is owned exactly once and the modelled
+    loads of the ranks stay within 10 % of each other up to 8 GPUs."""
+    from flake16_framework_b200 import hostprep as hp, scores as S, synth
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(3000, 16))
+    cfgs = S.all_config_keys()
+    gd = S.GridData(parsed, cfgs)
+    wanted, shards = S.plan_units(gd, cfgs, 10, world)
+    wanted2, shards2 = S.plan_units(gd, cfgs, 10, world)
+    assert shards == shards2                                    # deterministic
+    flat = [u for sh in shards for u in sh]
+    assert len(flat) == 120 and len(set(flat)) == 120
+    loads = [sum(S._unit_cost(gd, u, wanted[u[0]]) for u in sh) for sh in shards]
+    assert max(loads) <= 1.10 * (sum(loads) / world)
