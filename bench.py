@@ -11,8 +11,15 @@ preprocessings x 6 balancings x 3 models, 10-fold CV, 100-tree forests) over a s
   e2e   : `flake16_framework_b200.scores.write_scores("tests.json" -> "scores.pkl")`, i.e. the
           reference CLI path: JSON parse, host preprocessing, H2D of every dataset, the grid,
           D2H of the counts, pickle.
-With N > 1 ranks the (dataset, fold) units are sharded over ranks (strong scaling: the grid is
-fixed) and the counts are all-reduced once.
+With N > 1 ranks the (dataset, fold, balancing group) work items are sharded over ranks (strong
+scaling: the grid is fixed) and the counts are all-reduced once.
+
+The CPU arm (`--impl reference`, and the `cpu_baseline` object of our own line at N = 1) is ONE
+fixed sample, independent of --steps: fold 1 of 10 of all 18 (balancing x model) kinds on one
+Flake16 dataset and on one FlakeFlagger dataset = 36 single-fold tasks through the oracle
+(oracle/ref_scores.py: the reference's get_scores on the in-image scikit-learn), one
+single-threaded process per task like the reference's Pool(N_PROC) (experiment.py:47,496),
+extrapolated to the 216-config grid with the grid's own multiplicities (cpu_grid_estimate).
 """
 import argparse
 import json
@@ -30,6 +37,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "configs/sec for full `scores` grid"
 UNIT = "configs/s"
+BALANCINGS = ("None", "Tomek Links", "SMOTE", "ENN", "SMOTE ENN", "SMOTE Tomek")
+MODELS = ("Extra Trees", "Random Forest", "Decision Tree")
 
 
 def parse_args():
@@ -39,19 +48,37 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-tests", type=int, default=100000)
+    ap.add_argument("--n-estimators", type=int, default=100)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("F16_STREAMS", "4")))
-    ap.add_argument("--configs", default="grid216", help="grid216 | slice (1 dataset, 18 configs; for quick checks)")
+    ap.add_argument("--configs", default="grid216",
+                    help="grid216 | slice (1 dataset, 18 configs) | config5 (BASELINE configs[4]: the 12 datasets x "
+                         "SMOTE ENN x Extra Trees; use with --n-tests 1000000 --n-estimators 500)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probes", action="store_true", help="skip the single-kernel roofline probes")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0,
+                    help="reference arm: stop repeating the CPU sample when the next repetition would pass this budget")
     return ap.parse_args()
 
 
+def select_configs(all_keys, which):
+    if which == "slice":
+        return [c for c in all_keys if c[:3] == ("NOD", "Flake16", "Scaling")]
+    if which == "config5":
+        return [c for c in all_keys if c[3] == "SMOTE ENN" and c[4] == "Extra Trees"]
+    return list(all_keys)
+
+
 def workload_config(args):
-    return {"workload": "full scores grid: 216 configs x 10-fold CV, 100-tree forests, synthetic tests.json "
-                        "%d tests x 16 features (seed 16)" % args.n_tests if args.configs == "grid216" else
-                        "grid slice NOD/Flake16/Scaling: 18 configs x 10-fold, %d tests" % args.n_tests,
-            "n_tests": args.n_tests, "n_configs": 216 if args.configs == "grid216" else 18, "n_splits": 10,
-            "n_estimators": 100, "parallelism": "grid-sharded x%d" % args.gpus,
+    names = {"grid216": "full scores grid: 216 configs x 10-fold CV, %d-tree forests" % args.n_estimators,
+             "slice": "grid slice NOD/Flake16/Scaling: 18 configs x 10-fold CV, %d-tree forests" % args.n_estimators,
+             "config5": "BASELINE configs[4]: ExtraTrees n_estimators=%d + SMOTE-ENN on the 12 (flaky type, feature set, "
+                        "preprocessing) datasets x 10-fold CV" % args.n_estimators}
+    n_cfg = {"grid216": 216, "slice": 18, "config5": 12}[args.configs]
+    return {"workload": "%s, synthetic tests.json %d tests x 16 features (seed 16)" % (names[args.configs], args.n_tests),
+            "n_tests": args.n_tests, "n_configs": n_cfg, "n_splits": 10,
+            "n_estimators": args.n_estimators, "parallelism": "grid-sharded x%d" % args.gpus,
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -89,36 +116,49 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
-def cpu_sample(tests_file, steps_total):
-    """A bounded sample of the workload on the host cores through the oracle (the reference's
-    get_scores restated on the in-image scikit-learn), one single-threaded call chain per worker
-    like the reference's Pool(N_PROC).  Returns (config_equivalents, description, n_workers)."""
-    cores = os.cpu_count() or 1
-    base = [("NOD", "Flake16", "None", "None", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
-    smote = [("NOD", "Flake16", "None", "SMOTE", m) for m in ("Decision Tree", "Extra Trees", "Random Forest")]
-    if steps_total <= 2:
-        kinds = base + smote
-    elif steps_total <= 6:
-        kinds = base
-    else:
-        kinds = base[:2]
-    # fill the host: the same bounded task set replicated so that every core has one
-    # single-threaded call chain, exactly how the reference's Pool(N_PROC) loads the machine
-    workers = max(1, min(cores, 96))
-    reps = max(1, workers // len(kinds))
-    tasks = kinds * reps
-    desc = ("fold 1 of 10 of %d config kinds (%s) x %d replicas = %d single-fold tasks on the same tests.json, "
-            "one single-threaded process per task" % (len(kinds), "; ".join("/".join(t[2:]) for t in kinds), reps, len(tasks)))
-    return tasks, desc, min(workers, len(tasks))
+# The sample is FIXED (it does not depend on --steps / --warmup): fold 1 of all 18 (balancing x
+# model) kinds on the NOD / Flake16 / Scaling dataset (d = 16: brute-force k-NN in Tomek / ENN)
+# and on the NOD / FlakeFlagger / None dataset (d = 7: KD-tree k-NN) = 36 tasks.
+CPU_SAMPLE_DATASETS = (("NOD", "Flake16", "Scaling"), ("NOD", "FlakeFlagger", "None"))
 
 
-def run_cpu_sample(tests_file, tasks, workers):
+def cpu_sample_tasks():
+    return [ds + (bal, model) for ds in CPU_SAMPLE_DATASETS for bal in BALANCINGS for model in MODELS]
+
+
+def cpu_sample_desc(n_tests, n_estimators, workers):
+    return ("sample: fold 1 of 10 of all 18 (balancing x model) kinds on NOD/Flake16/Scaling and on NOD/FlakeFlagger/None "
+            "= 36 single-fold tasks of the %d-test tests.json (%d-tree forests), one single-threaded process per task "
+            "(%d at a time) through the oracle on scikit-learn; extrapolated to the 216-config grid: every sampled kind "
+            "stands for the 6 (flaky type x preprocessing) configs of its feature set, config time = setup + 10 x fold "
+            "time, grid time = sum of config times / min(host cores, 216) workers (perfect packing, the best case for "
+            "the reference's Pool(N_PROC))" % (n_tests, n_estimators, workers))
+
+
+def run_cpu_sample(tests_file, n_estimators=100):
+    """Runs the 36 tasks; returns (results, wall seconds, workers)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_scores as R
+    tasks = cpu_sample_tasks()
+    workers = max(1, min(os.cpu_count() or 1, len(tasks)))
     t0 = time.perf_counter()
-    R.run_configs(tasks, tests_file, processes=workers, max_folds=1)
-    dt = time.perf_counter() - t0
-    return (len(tasks) / 10.0) / dt, dt          # config-equivalents per second
+    res = R.run_configs_timed(tasks, tests_file, workers, n_splits=10, max_folds=1, n_estimators=n_estimators)
+    return res, time.perf_counter() - t0, workers
+
+
+def cpu_grid_estimate(results):
+    """216-config grid estimate from the 36-task sample (see cpu_sample_desc)."""
+    cores = os.cpu_count() or 1
+    pool = min(cores, 216)
+    cfg_s = {keys: t["setup_s"] + 10.0 * t["folds_s"] for keys, t, _, _ in results}
+    total_cpu_s = 6.0 * sum(cfg_s.values())
+    grid_s = total_cpu_s / pool
+    by_kind = {}
+    for keys, t, _, _ in results:
+        by_kind.setdefault("%s/%s" % (keys[3], keys[4]), []).append(round(t["folds_s"], 2))
+    return {"value": 216.0 / grid_s, "grid_s_estimate": grid_s, "cpu_core_s_estimate": total_cpu_s, "pool_workers": pool,
+            "slowest_config_s_estimate": max(cfg_s.values()),
+            "fold_s_by_kind[Flake16,FlakeFlagger]": by_kind}
 
 
 def reference_arm(args):
@@ -129,33 +169,65 @@ def reference_arm(args):
     tmp = tempfile.mkdtemp(prefix="f16bench_ref")
     tests_file = os.path.join(tmp, "tests.json")
     synth.make_tests_json(tests_file, args.n_tests, 16)
-    tasks, desc, workers = cpu_sample(tests_file, args.steps + args.warmup)
-    for _ in range(args.warmup):
-        run_cpu_sample(tests_file, tasks, workers)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        run_cpu_sample(tests_file, tasks, workers)
-    dt = time.perf_counter() - t0
-    value = (len(tasks) / 10.0) * args.steps / dt
+    # W warm-up + K timed repetitions of the fixed sample, as far as the time budget allows:
+    # one repetition takes as long as its slowest task (a RandomForest on SMOTE'd rows after a
+    # brute-force k-NN: minutes), so the steps ACTUALLY run are printed.
+    t_begin = time.perf_counter()
+    runs = []
+    warm_done = 0
+    requested = args.warmup + args.steps
+    last = 0.0
+    for i in range(requested):
+        if runs and (time.perf_counter() - t_begin) + last > args.cpu_budget_s:
+            break
+        res, wall, workers = run_cpu_sample(tests_file, args.n_estimators)
+        last = wall
+        runs.append((res, wall, workers))
+    if len(runs) > args.steps:          # the first ones count as warm-up
+        warm_done = len(runs) - args.steps
+    timed = runs[warm_done:]
+    ests = [cpu_grid_estimate(r) for r, _, _ in timed]
+    value = sum(e["value"] for e in ests) / len(ests)
+    workers = timed[0][2]
+    wall = sum(w for _, w, _ in timed) / len(timed)
+    est = ests[-1]
+    cfg = workload_config(args)
+    cfg["workload"] = cpu_sample_desc(args.n_tests, args.n_estimators, workers) + " | stands for: " + cfg["workload"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc,
-                             "host_cores": os.cpu_count()},
+            "steps": len(timed), "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": cpu_sample_desc(args.n_tests, args.n_estimators, workers) + " (%.0f s per repetition)" % wall,
+                             "host_cores": os.cpu_count(), "estimate": est},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------ our arm
-def roofline_probe(parsed, L):
-    """Dominant tree kernel (k_build_best, RandomForest 100 trees on one 90 000 x 16 fold):
-    algorithmic bytes per launch = 12 B x sum_{internal nodes} n_node_samples x (F_eval + 1)
-    (SURVEY.md 8(d)), F_eval = max_features = 4; duration = CUDA events around that kernel on
-    its launch stream (inside f16_forest_fit)."""
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _traffic(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
+def tree_roofline_probe(parsed, L, kind_name):
+    """One tree-building kernel alone (100 trees on one 90 000 x 16 fold): algorithmic bytes per launch
+    = 12 B x sum_{internal nodes} n_node_samples x (F_eval + 1), F_eval =
+    max_features = 4, read off the fitted trees; duration = CUDA events around that kernel on its
+    launch stream (inside f16_forest_fit)."""
     import numpy as np
     import torch
     from flake16_framework_b200 import hostprep as hp, ops
+    kind = {"RF": ops.KIND_RF, "ET": ops.KIND_ET}[kind_name]
     X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY, hp.FEATURE_SETS["Flake16"])
     X = np.ascontiguousarray(X)
     tr, _ = next(iter(hp.kfold_split(hp.stratified_kfold_test_folds(y))))
@@ -168,7 +240,7 @@ def roofline_probe(parsed, L):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for it in range(4):
         flush.fill_(it)
-        f = ops.forest_fit(Xrow, ytr, 16, ops.KIND_RF, 100, 0, sidx)
+        f = ops.forest_fit(Xrow, ytr, 16, kind, 100, 0, sidx)
         t = L.f16_forest_build_ms(f._h)
         if it > 0:
             ms.append(t)
@@ -181,30 +253,28 @@ def roofline_probe(parsed, L):
             alg = 12.0 * tot * (4 + 1)
         f.free()
     L.f16_set_profiling(0)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = _peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_ms = sum(ms) / len(ms)
     achieved = alg / (avg_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_build_best_bytes_per_launch")
-    except Exception:
-        pass
-    return {"bound": "hbm", "kernel": "k_build_best<16> (RandomForest, 100 trees, 90000x16 fold)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-            "algorithmic_bytes_per_launch": alg, "kernel_ms": avg_ms, "traffic": traffic}
+    kname = {"RF": "k_build_best_rf<16> (RandomForest", "ET": "k_build_random_et<16> (ExtraTrees"}[kind_name]
+    out = {"bound": "hbm", "kernel": kname + ", 100 trees, 90000x16 fold, timed alone)",
+           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+           "algorithmic_bytes_per_launch": alg, "kernel_ms": avg_ms,
+           "traffic": _traffic("k_build_best_bytes_per_launch" if kind_name == "RF" else "k_build_random_dram_bytes_per_launch")}
+    if kind_name == "ET":
+        out["traffic_l2_to_l1"] = _traffic("k_build_random_l2_to_l1_bytes_per_launch")
+        out["note"] = ("the training rows (5.8 MB) stay L2-resident: DRAM traffic is ~1 % of the algorithmic bytes, the "
+                       "kernel's memory traffic is L2->L1 gathers; it is bound by per-node latency chains, not by HBM")
+    return out
 
 
 def knn_roofline_probe(parsed):
-    """Second kernel reported against a roofline: the tensor-core k-NN filter (tcgen05 + TMEM).
-    Algorithmic flops = 3 d n_query n_ref; duration = CUDA events around the whole
-    f16_knn call (centring, float16 split, filter, exact float64 selection) on one standardised
-    90 000 x 16 fold; peak = measured dense bf16 tensor throughput."""
+    """The tensor-core k-NN filter (tcgen05 + TMEM).  Algorithmic flops = 3 d n_query n_ref
+    (SURVEY.md 8(d)); duration = CUDA events around the whole f16_knn call (centring, float16 split,
+    filter, exact float64 selection) on one standardised 90 000 x 16 fold; peak = measured dense
+    bf16 tensor throughput."""
     import numpy as np
     import torch
     from flake16_framework_b200 import hostprep as hp, ops
@@ -224,25 +294,38 @@ def knn_roofline_probe(parsed):
         e1.synchronize()
         if it > 0:
             ms.append(e0.elapsed_time(e1))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("bf16_tflops", 1800.0))
+    peaks = _peaks()
+    peak = float(peaks.get("bf16_tflops", 1590.0))
     n = A.shape[0]
     flops = 3.0 * 16 * n * n
     avg_ms = sum(ms) / len(ms)
     achieved = flops / (avg_ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "f16_knn strategy 3: k_knn_umma_filter (tcgen05) + exact float64 select, %d x %d x 16" % (n, n),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops (measured)" if peaks else "fallback 1800 TFLOP/s",
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (measured)" if peaks else "fallback 1590 TFLOP/s",
             "algorithmic_flops_per_call": flops, "call_ms": avg_ms, "traffic": None,
             "note": "the filter is bound by its per-element epilogue (one compare per distance), not by the MMA rate"}
 
 
+def parity_check(cpu_results, S, parsed, dev, n_streams, n_estimators):
+    """The CPU sample's fold-1 counts (oracle) against this library's counts for the same 36
+    (config, fold) pairs at the bench's own size, per project and in total."""
+    tasks = [keys for keys, _, _, _ in cpu_results]
+    cfgs, counts, _, gd = S.run_grid(parsed, tasks, n_streams=n_streams, device=dev, n_estimators=n_estimators,
+                                     return_counts=True, folds=[0])
+    bad = []
+    for keys, _, per_proj, total in cpu_results:
+        ci = cfgs.index(keys)
+        ours_total = [int(v) for v in counts[ci, gd.n_proj]]
+        ours_proj = {str(name): [int(v) for v in counts[ci, pid]] for pid, name in enumerate(gd.proj_names)}
+        if ours_total != total or ours_proj != per_proj:
+            bad.append({"config": list(keys), "cpu_total_fp_fn_tp": total, "gpu_total_fp_fn_tp": ours_total})
+    return {"configs": len(tasks), "folds": 1, "n_tests": int(len(parsed[1])), "identical": not bad,
+            "what": "FP/FN/TP per project and in total, oracle (scikit-learn + samplers_np) vs GPU, fold 1 of each sampled config",
+            "mismatches": bad[:8]}
+
+
 def ours_arm(args):
-    import numpy as np
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +334,7 @@ def ours_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # the driver's own setting (e.g. INFO) wins
         dist.init_process_group("nccl", device_id=dev)
     from flake16_framework_b200 import _lib, hostprep as hp, scores as S, synth
     L = _lib.lib()
@@ -261,9 +344,7 @@ def ours_arm(args):
     tests_file = os.path.join(tmp, "tests.json")
     synth.make_tests_json(tests_file, args.n_tests, 16)          # every rank: same seeded table
     parsed = hp.parse_tests(tests_file)
-    configs = S.all_config_keys()
-    if args.configs == "slice":
-        configs = [c for c in configs if c[:3] == ("NOD", "Flake16", "Scaling")]
+    configs = select_configs(S.all_config_keys(), args.configs)
     prepared = S.prepare(parsed, configs, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -276,7 +357,7 @@ def ours_arm(args):
 
     def one_step():
         return S.run_grid(parsed, configs, n_streams=args.streams, device=dev, rank=rank, world=world,
-                          prepared=prepared, return_counts=True)
+                          n_estimators=args.n_estimators, prepared=prepared, return_counts=True)
 
     for _ in range(args.warmup):
         one_step()
@@ -298,6 +379,12 @@ def ours_arm(args):
         total_ms += ev0.elapsed_time(ev1)
     launches = int(L.f16_launch_count(0))
     clocks = sampler.stop() if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    try:        # the library's scratch lives in the CUDA stream-ordered pool, not in torch's allocator
+        free_b, total_b = torch.cuda.mem_get_info(dev)
+        peak_mem = max(peak_mem, total_b - free_b)
+    except Exception:
+        pass
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     ln = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
@@ -308,13 +395,13 @@ def ours_arm(args):
     n_cfg = len(configs)
     value = n_cfg * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: tests.json on disk -> scores.pkl through the public write_scores()
+    # ---- e2e: tests.json on disk -> scores.pkl through the public write_scores(); a couple of steps
+    #      (everything is warm by now; the path differs from `value` by host parsing + H2D + pickle)
     e2e = None
     if not args.no_e2e:
         scores_file = os.path.join(tmp, "scores.pkl")
-        kw = dict(n_streams=args.streams, configs=configs)
-        S.write_scores(tests_file, scores_file, **kw)                # warm
-        e2e_steps = args.steps if total_ms / args.steps < 30e3 else 1
+        kw = dict(n_streams=args.streams, configs=configs, n_estimators=args.n_estimators)
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
         barrier()
         t0 = time.perf_counter()
         stats = None
@@ -330,31 +417,45 @@ def ours_arm(args):
                "includes": "json parse, host preprocessing, H2D, grid, D2H, pickle"}
 
     if rank != 0:
-        return
+        return 0
+    trees_per_fit = args.n_estimators
+    n_forest_cfg = sum(1 for c in configs if c[4] != "Decision Tree")
+    n_dt_cfg = n_cfg - n_forest_cfg
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 criterion / f32 features / int counts",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(ln.item()),
-            "trees_per_s": (n_cfg // 3) * 10 * 201 * args.steps / (total_ms * 1e-3) if args.configs == "grid216" else None}
+            "trees_per_s": (n_forest_cfg * trees_per_fit + n_dt_cfg) * 10 * args.steps / (total_ms * 1e-3),
+            "device_memory_in_use_bytes": int(peak_mem)}
+    rc = 0
     if world == 1:
-        line["roofline"] = roofline_probe(parsed, L)
-        line["roofline_knn"] = knn_roofline_probe(parsed)
+        if not args.no_probes:
+            line["roofline"] = tree_roofline_probe(parsed, L, "RF")
+            line["roofline_et"] = tree_roofline_probe(parsed, L, "ET")
+            line["roofline_knn"] = knn_roofline_probe(parsed)
         if not args.no_cpu_baseline:
-            tasks, desc, workers = cpu_sample(tests_file, 1)
-            v, dt = run_cpu_sample(tests_file, tasks, workers)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
-                                    "sample": desc + " (%.1f s)" % dt, "host_cores": os.cpu_count()}
+            res, wall, workers = run_cpu_sample(tests_file, args.n_estimators)
+            est = cpu_grid_estimate(res)
+            line["cpu_baseline"] = {"value": est["value"], "unit": UNIT, "cores": workers, "kind": "port",
+                                    "sample": cpu_sample_desc(args.n_tests, args.n_estimators, workers) + " (%.0f s)" % wall,
+                                    "host_cores": os.cpu_count(), "estimate": est}
+            line["parity_check"] = parity_check(res, S, parsed, dev, args.streams, args.n_estimators)
+            if not line["parity_check"]["identical"]:
+                rc = 1
     print(json.dumps(line), flush=True)
+    return rc
 
 
 if __name__ == "__main__":
     a = parse_args()
+    rc = 0
     if a.impl == "reference":
         reference_arm(a)
     else:
-        ours_arm(a)
+        rc = ours_arm(a) or 0
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         if dist.is_initialized():
             dist.destroy_process_group()
+    sys.exit(rc)

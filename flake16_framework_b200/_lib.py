@@ -29,8 +29,6 @@ def _sources(tune):
         ("f16_tree_random.cu", "_et", ["-fmad=false", "-DF16_VARIANT=_et", "-DNT=%d" % t["ET_NT"],
                                         "-DF16_MINB=%d" % t["ET_MINB"], "-DF16_S16=%d" % t["ET_S16"],
                                         "-DF16_S8=%d" % t["ET_S8"]] + x),
-        ("f16_tree_random_w.cu", "", ["-fmad=false", "-DF16_WS16=%d" % t.get("ET_WS16", 64),
-                                      "-DF16_WS8=%d" % t.get("ET_WS8", 128)]),
         ("f16_tree_best.cu", "_rf", ["-fmad=false", "-DF16_VARIANT=_rf", "-DNT=%d" % t["RF_NT"],
                                       "-DF16_MINB=%d" % t["RF_MINB"], "-DF16_WITH_BOOTSTRAP"] + x),
         ("f16_tree_best.cu", "_dt", ["-fmad=false", "-DF16_VARIANT=_dt", "-DNT=%d" % t["DT_NT"],
@@ -38,7 +36,6 @@ def _sources(tune):
         ("f16_misc.cu", "", ["-fmad=false"]),
         ("f16_sort.cu", "", []),
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
-        ("f16_knn32.cu", "", []),
         ("f16_knn_tc.cu", "", ["-DTC_MT=%d" % t.get("TC_MT", 2)]),
         ("f16_knn_sweep.cu", "", []),
         ("f16_knn_umma.cu", "", ["-DUM_NB=%d" % t.get("UM_NB", 2), "-DUM_STAGES=%d" % t.get("UM_STAGES", 4)]),
@@ -102,14 +99,18 @@ SIGNATURES = {
     "f16_gather_rows_f32": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_gather_rows_f64": ([c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_gather_u8": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "f16_gather_i32": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_argsort_columns": ([c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
     "f16_tree_seeds": ([c_uint32, c_int32, c_int32, c_void_p, c_void_p], c_int),
     "f16_bootstrap_counts": ([c_void_p, c_int32, c_int64, c_void_p, c_void_p], c_int),
     "f16_forest_fit": ([c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32,
                         c_uint32, c_void_p, ctypes.POINTER(c_void_p)], c_int),
+    "f16_forest_fit_cap": ([c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                            c_uint32, c_int64, c_void_p, ctypes.POINTER(c_void_p)], c_int),
     "f16_forest_predict": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "f16_forest_status": ([c_void_p, c_void_p], c_int),
     "f16_forest_n_trees": ([c_void_p], c_int),
+    "f16_forest_max_nodes": ([c_void_p], c_int),
     "f16_forest_node_counts": ([c_void_p, c_void_p, c_void_p], c_int),
     "f16_forest_export": ([c_void_p, c_int32, c_int64] + [c_void_p] * 8 + [c_void_p], c_int),
     "f16_forest_free": ([c_void_p, c_void_p], None),

@@ -42,8 +42,6 @@ extern "C" void f16_set_error(const char* fmt, ...);
 
 struct KnnPerm { int c[F16_MAX_D]; };
 
-int f16_knn32_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
-                     float* c32, double* an, cudaStream_t st);
 int f16_knn_tc_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
                       cudaStream_t st);
 int f16_knn_umma_launch(const double* A, int n, const double* Q, int nq, int d, int k, const int* perm, int32_t* out,
@@ -260,16 +258,7 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
         }
         prefix_test = 0;
     }
-    if (prefix_test == 2) {     // float32 conservative filter (f16_knn32.cu); falls through if unsupported
-        float* c32 = nullptr; double* an = nullptr;
-        CUDA_TRY(cudaMallocAsync((void**)&c32, sizeof(float) * (size_t)n * F16_MAX_D, st));
-        CUDA_TRY(cudaMallocAsync((void**)&an, sizeof(double) * (size_t)n, st));
-        int r32 = f16_knn32_launch(A_dev, (int)n, Q_dev, (int)nq, d, k, pm.c, idx_dev, c32, an, st);
-        CUDA_TRY(cudaFreeAsync(c32, st));
-        CUDA_TRY(cudaFreeAsync(an, st));
-        if (r32 == F16_OK) { CUDA_TRY(cudaGetLastError()); return F16_OK; }
-        prefix_test = 0;
-    }
+    if (prefix_test == 2) prefix_test = 0;      // (strategy 2, a float32 filter, was measured never faster and is no longer built)
     double* nrm = nullptr;      // reference rows in tile layout (norms + permuted coordinates)
     CUDA_TRY(cudaMallocAsync((void**)&nrm, sizeof(double) * (size_t)n * (F16_MAX_D + 2), st));
     int rc;
@@ -280,8 +269,12 @@ extern "C" int f16_knn(const double* A_dev, int64_t n, const double* Q_dev, int6
 #undef CASE_D
         default: rc = F16_ERR_INVALID;
     }
+    cudaError_t le = cudaGetLastError();
+    cudaError_t fe = cudaFreeAsync(nrm, st);             // released on every path, failed launches included
     if (rc) { f16_set_error("f16_knn: unsupported (d=%d, k=%d)", d, k); return rc; }
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(nrm, st));
+    if (le != cudaSuccess || fe != cudaSuccess) {
+        f16_set_error("f16_knn: %s", cudaGetErrorString(le != cudaSuccess ? le : fe));
+        return F16_ERR_CUDA;
+    }
     return F16_OK;
 }

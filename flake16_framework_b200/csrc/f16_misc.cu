@@ -132,6 +132,19 @@ extern "C" int f16_gather_u8(const uint8_t* y_dev, const int64_t* idx_dev, int64
     return F16_OK;
 }
 
+__global__ void k_gather_i32(const int32_t* __restrict__ v, const int64_t* __restrict__ idx, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v[idx[i]];
+}
+extern "C" int f16_gather_i32(const int32_t* v_dev, const int64_t* idx_dev, int64_t n_out, int32_t* out_dev, void* stream) {
+    if (!v_dev || !out_dev || !idx_dev || n_out < 0) { f16_set_error("f16_gather_i32: bad arguments"); return F16_ERR_INVALID; }
+    if (n_out == 0) return F16_OK;
+    k_gather_i32<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v_dev, idx_dev, n_out, out_dev);
+    f16_count_launch(1);
+    CUDA_TRY(cudaGetLastError());
+    return F16_OK;
+}
+
 // ------------------------------------------------------------------ SMOTE interpolation
 // X_new[j] = C[row] + step[j] * (C[nn[row][1 + col]] - C[row]),  row = idx[j] / k, col = idx[j] % k
 // (imblearn/over_sampling/_smote/base.py _make_samples/_generate_samples); nn has k+1

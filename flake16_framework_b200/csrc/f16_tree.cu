@@ -28,13 +28,18 @@ extern "C" cudaError_t f16_malloc_async(void** p, size_t bytes, cudaStream_t st)
 // walk: blockIdx.y = tree, threads over rows; leaf class sums -> leaf[tree][row]
 template <int DP>
 __global__ void __launch_bounds__(256) k_predict_walk(const F16Node* __restrict__ nodes, int node_cap,
+                                                      const int32_t* __restrict__ node_count,
                                                       const float* __restrict__ X, int n, int2* __restrict__ leaf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const F16Node* tn = nodes + (size_t)blockIdx.y * node_cap;
+    const int nc = node_count[blockIdx.y];
     const float* row = X + (size_t)i * DP;
     int id = 0;
-    while (true) {
+    // a complete tree never leaves [0, nc) and is at most F16_STACK_CAP deep; a tree whose fit was
+    // aborted (capacity overflow, reported by f16_forest_status) may hold dangling links - the
+    // bounds keep the walk inside the tree's records and finite, its output is then meaningless
+    for (int step = 0; step <= F16_STACK_CAP && id >= 0 && id < nc; step++) {
         const int4* pn = reinterpret_cast<const int4*>(tn + id);
         int4 a = __ldg(pn);       // thr (2 words), feature, right
         if (a.z < 0) {
@@ -46,6 +51,7 @@ __global__ void __launch_bounds__(256) k_predict_walk(const F16Node* __restrict_
         float v = __ldg(row + a.z);
         id = ((double)v <= thr) ? id + 1 : a.w;
     }
+    leaf[(size_t)blockIdx.y * n + i] = make_int2(1, 0);
 }
 
 // reduce: per row, sum tree probabilities IN TREE ORDER (sklearn/ensemble/_forest.py:704-717,
@@ -107,10 +113,36 @@ extern "C" int f16_bootstrap_counts(const uint32_t* tree_seed_host, int32_t n_tr
     return F16_OK;
 }
 
-extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
-                              const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
-                              int32_t max_features, uint32_t seed, void* stream, f16_forest** out) {
-    cudaStream_t st = (cudaStream_t)stream;
+// Everything a fit allocates besides the forest itself; released (stream-ordered) on every path.
+struct FitScratch {
+    cudaStream_t st;
+    void* p[8];
+    int np;
+    explicit FitScratch(cudaStream_t s) : st(s), np(0) {}
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = f16_malloc_async(out, bytes, st);
+        if (e == cudaSuccess) p[np++] = *out;
+        return e;
+    }
+    ~FitScratch() { for (int i = 0; i < np; i++) cudaFreeAsync(p[i], st); }
+};
+
+static void forest_release(f16_forest* F, cudaStream_t st) {
+    if (!F) return;
+    if (F->nodes) cudaFreeAsync(F->nodes, st);
+    if (F->node_count) cudaFreeAsync(F->node_count, st);
+    if (F->err) cudaFreeAsync(F->err, st);
+    if (F->has_ev) { cudaEventDestroy(F->ev0); cudaEventDestroy(F->ev1); }
+    free(F);
+}
+
+// node_cap: capacity of one tree's node array.  A binary tree over n rows has at most 2n - 1
+// nodes; callers that know better (f16_forest_fit_cap: a measured count of an earlier fit on a
+// training set of the same kind) pass a smaller capacity, and a tree that outgrows it fails the
+// fit with F16_ERR_OVERFLOW (f16_forest_status) instead of writing out of bounds.
+static int forest_fit_impl(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
+                           const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
+                           int32_t max_features, uint32_t seed, int64_t node_cap, cudaStream_t st, f16_forest** out) {
     if (!X_dev || !y_dev || !out || n < 1 || n > F16_MAX_ROWS - 1 || d < 1 || d > F16_MAX_D) {
         f16_set_error("f16_forest_fit: bad arguments (n=%lld d=%d)", (long long)n, d);
         return F16_ERR_INVALID;
@@ -128,8 +160,10 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     if (rc) return rc;
 
     f16_forest* F = (f16_forest*)calloc(1, sizeof(f16_forest));
+    if (!F) { f16_set_error("f16_forest_fit: out of host memory"); return F16_ERR_NOMEM; }
     F->kind = kind; F->n_trees = n_trees; F->d = d; F->dp = dp; F->n_train = n;
-    F->node_cap = (int)(2 * n - 1);
+    const int64_t full_cap = 2 * n - 1;
+    F->node_cap = (int)((node_cap > 0 && node_cap < full_cap) ? node_cap : full_cap);
     if (F->node_cap < 1) F->node_cap = 1;
 
     F16FitParams P;
@@ -137,59 +171,87 @@ extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t 
     P.X = X_dev; P.y = y_dev; P.sorted_idx = sorted_idx_dev;
     P.n = (int)n; P.d = d; P.dp = dp; P.n_trees = n_trees; P.max_features = max_features;
     P.stack_cap = F16_STACK_CAP; P.node_cap = F->node_cap;
+    static unsigned launch_serial = 0;
+    P.salt = (int)(__sync_fetch_and_add(&launch_serial, 1u) * 7u);
 
+    FitScratch S(st);           // freed when this function returns, whatever the path
+#define FIT_TRY(x)                                                                             \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            f16_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            forest_release(F, st);                                                             \
+            return e_ == cudaErrorMemoryAllocation ? F16_ERR_NOMEM : F16_ERR_CUDA;             \
+        }                                                                                      \
+    } while (0)
     uint32_t* rr_dev = nullptr; uint8_t* bw = nullptr;
-    CUDA_TRY(f16_malloc_async((void**)&F->nodes, sizeof(F16Node) * (size_t)n_trees * F->node_cap, st));
-    CUDA_TRY(f16_malloc_async((void**)&F->node_count, sizeof(int32_t) * n_trees, st));
-    CUDA_TRY(f16_malloc_async((void**)&F->err, sizeof(int32_t), st));
-    CUDA_TRY(cudaMemsetAsync(F->err, 0, sizeof(int32_t), st));
-    CUDA_TRY(cudaMemsetAsync(F->node_count, 0, sizeof(int32_t) * n_trees, st));
-    CUDA_TRY(f16_malloc_async((void**)&rr_dev, sizeof(uint32_t) * n_trees, st));
-    CUDA_TRY(cudaMemcpyAsync(rr_dev, rr.data(), sizeof(uint32_t) * n_trees, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(f16_malloc_async((void**)&P.stack, sizeof(F16StackRec) * (size_t)n_trees * P.stack_cap, st));
+    FIT_TRY(f16_malloc_async((void**)&F->nodes, sizeof(F16Node) * (size_t)n_trees * F->node_cap, st));
+    FIT_TRY(f16_malloc_async((void**)&F->node_count, sizeof(int32_t) * n_trees, st));
+    FIT_TRY(f16_malloc_async((void**)&F->err, 2 * sizeof(int32_t), st));
+    FIT_TRY(cudaMemsetAsync(F->err, 0, 2 * sizeof(int32_t), st));
+    FIT_TRY(cudaMemsetAsync(F->node_count, 0, sizeof(int32_t) * n_trees, st));
+    FIT_TRY(S.alloc((void**)&rr_dev, sizeof(uint32_t) * n_trees));
+    FIT_TRY(cudaMemcpyAsync(rr_dev, rr.data(), sizeof(uint32_t) * n_trees, cudaMemcpyHostToDevice, st));
+    FIT_TRY(S.alloc((void**)&P.stack, sizeof(F16StackRec) * (size_t)n_trees * P.stack_cap));
     size_t buf_words = (size_t)n_trees * 2 * (best ? (size_t)d : 1) * (size_t)n;
-    CUDA_TRY(f16_malloc_async((void**)&P.buf, sizeof(uint32_t) * buf_words, st));
+    FIT_TRY(S.alloc((void**)&P.buf, sizeof(uint32_t) * buf_words));
     P.rand_r_state = rr_dev; P.nodes = F->nodes; P.node_count = F->node_count; P.err = F->err;
 
     if (kind == F16_KIND_RF) {
         size_t stride = align_up((size_t)n, 4);
-        CUDA_TRY(f16_malloc_async((void**)&bw, stride * n_trees, st));
-        rc = f16_bootstrap_counts(tree_seed.data(), n_trees, n, bw, stream);
-        if (rc) return rc;
+        FIT_TRY(S.alloc((void**)&bw, stride * n_trees));
+        rc = f16_bootstrap_counts(tree_seed.data(), n_trees, n, bw, (void*)st);
+        if (rc) { forest_release(F, st); return rc; }
         P.boot_w = bw;
     }
     size_t dyn = 0;
     if (best) {
-        CUDA_TRY(f16_malloc_async((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n, st));
+        FIT_TRY(S.alloc((void**)&P.lid, sizeof(uint32_t) * (size_t)n_trees * (size_t)n));
         P.side_words = (int)((n + 31) / 32);
         // F16_FORCE_GLOBAL_SIDE=1 exercises the > 524288-row path on small inputs (tests)
         static const int force_global_side = getenv("F16_FORCE_GLOBAL_SIDE") ? atoi(getenv("F16_FORCE_GLOBAL_SIDE")) : 0;
         if (P.side_words > F16_SIDE_SMEM_MAX_WORDS || force_global_side) {
-            CUDA_TRY(f16_malloc_async((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words, st));
+            FIT_TRY(S.alloc((void**)&P.side_global, sizeof(uint32_t) * (size_t)n_trees * P.side_words));
         } else {
             dyn = sizeof(uint32_t) * (size_t)P.side_words;
         }
     }
     if (f16_get_profiling()) {
-        CUDA_TRY(cudaEventCreate(&F->ev0));
-        CUDA_TRY(cudaEventCreate(&F->ev1));
+        FIT_TRY(cudaEventCreate(&F->ev0));
+        cudaError_t e1 = cudaEventCreate(&F->ev1);
+        if (e1 != cudaSuccess) { cudaEventDestroy(F->ev0); FIT_TRY(e1); }
         F->has_ev = 1;
-        CUDA_TRY(cudaEventRecord(F->ev0, st));
+        FIT_TRY(cudaEventRecord(F->ev0, st));
     }
-    static const int et_warp = getenv("F16_ET_WARP") ? atoi(getenv("F16_ET_WARP")) : 0;
-    rc = (kind == F16_KIND_ET) ? (et_warp ? f16_launch_build_random_w(P, st) : f16_launch_build_random_et(P, st))
+    rc = (kind == F16_KIND_ET) ? f16_launch_build_random_et(P, st)
        : (kind == F16_KIND_RF) ? f16_launch_build_best_rf(P, dyn, st) : f16_launch_build_best_dt(P, dyn, st);
-    if (rc) { f16_set_error("tree build kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
-    if (F->has_ev) CUDA_TRY(cudaEventRecord(F->ev1, st));
-    CUDA_TRY(cudaFreeAsync(P.buf, st));
-    CUDA_TRY(cudaFreeAsync(P.stack, st));
-    CUDA_TRY(cudaFreeAsync(rr_dev, st));
-    if (bw) CUDA_TRY(cudaFreeAsync(bw, st));
-    if (P.side_global) CUDA_TRY(cudaFreeAsync(P.side_global, st));
-    if (P.lid) CUDA_TRY(cudaFreeAsync(P.lid, st));
-    if (P.cmp) CUDA_TRY(cudaFreeAsync(P.cmp, st));
+    if (rc) {
+        f16_set_error("tree build kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        forest_release(F, st);
+        return rc;
+    }
+    if (F->has_ev) FIT_TRY(cudaEventRecord(F->ev1, st));
+#undef FIT_TRY
     *out = F;
     return F16_OK;
+}
+
+extern "C" int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
+                              const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
+                              int32_t max_features, uint32_t seed, void* stream, f16_forest** out) {
+    return forest_fit_impl(X_dev, y_dev, n, d, sorted_idx_dev, kind, n_estimators, max_features, seed, 0,
+                           (cudaStream_t)stream, out);
+}
+
+// Same fit with an explicit per-tree node capacity (0 = the 2n - 1 worst case).  The worst case
+// costs 32 B x (2n - 1) per tree - 57 GB for a 500-tree forest on 1.8 M rows - while real trees
+// of this path hold 0.05 n - 0.15 n nodes; the grid engine passes a capacity derived from the
+// node counts it has measured and retries with the worst case if a fit reports F16_ERR_OVERFLOW.
+extern "C" int f16_forest_fit_cap(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
+                                  const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
+                                  int32_t max_features, uint32_t seed, int64_t node_cap, void* stream, f16_forest** out) {
+    return forest_fit_impl(X_dev, y_dev, n, d, sorted_idx_dev, kind, n_estimators, max_features, seed, node_cap,
+                           (cudaStream_t)stream, out);
 }
 
 extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64_t n, uint8_t* pred_dev, void* stream) {
@@ -199,8 +261,8 @@ extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64
     int2* leaf = nullptr;
     CUDA_TRY(f16_malloc_async((void**)&leaf, sizeof(int2) * (size_t)F->n_trees * n, st));
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)F->n_trees);
-    if (F->dp == 8) k_predict_walk<8><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);
-    else k_predict_walk<16><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, X_dev, (int)n, leaf);
+    if (F->dp == 8) k_predict_walk<8><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, F->node_count, X_dev, (int)n, leaf);
+    else k_predict_walk<16><<<grid, 256, 0, st>>>(F->nodes, F->node_cap, F->node_count, X_dev, (int)n, leaf);
     CUDA_TRY(cudaGetLastError());
     k_predict_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(leaf, (int)n, F->n_trees, pred_dev);
     f16_count_launch(2);
@@ -212,14 +274,17 @@ extern "C" int f16_forest_predict(const f16_forest* F, const float* X_dev, int64
 // Synchronises `stream` and returns the device-side status of the fit (0 ok).
 extern "C" int f16_forest_status(const f16_forest* F, void* stream) {
     if (!F) { f16_set_error("f16_forest_status: null forest"); return F16_ERR_INVALID; }
-    int32_t e = 0;
-    CUDA_TRY(cudaMemcpyAsync(&e, F->err, sizeof(e), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int32_t ev[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(ev, F->err, sizeof(ev), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    const int32_t e = ev[0];
+    const_cast<f16_forest*>(F)->max_nodes = ev[1];
     if (e) f16_set_error("forest fit failed on device: code %d (node/stack capacity or bootstrap weight > 127)", e);
     return e;
 }
 
 extern "C" int f16_forest_n_trees(const f16_forest* F) { return F ? F->n_trees : 0; }
+extern "C" int f16_forest_max_nodes(const f16_forest* F) { return F ? F->max_nodes : 0; }
 
 // Synchronises on the build kernel's end event; milliseconds spent in the tree-building
 // kernel alone (needs f16_set_profiling(1) before the fit), or -1.
@@ -265,12 +330,4 @@ extern "C" int f16_forest_export(const f16_forest* F, int32_t tree, int64_t n_no
     return F16_OK;
 }
 
-extern "C" void f16_forest_free(f16_forest* F, void* stream) {
-    if (!F) return;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (F->nodes) cudaFreeAsync(F->nodes, st);
-    if (F->node_count) cudaFreeAsync(F->node_count, st);
-    if (F->err) cudaFreeAsync(F->err, st);
-    if (F->has_ev) { cudaEventDestroy(F->ev0); cudaEventDestroy(F->ev1); }
-    free(F);
-}
+extern "C" void f16_forest_free(f16_forest* F, void* stream) { forest_release(F, (cudaStream_t)stream); }

@@ -37,9 +37,9 @@ struct F16FitParams {
     int32_t* node_count;        // [n_trees]
     uint32_t* side_global;      // [n_trees][ceil(n/32)] or nullptr (side bits live in smem)
     uint32_t* lid;              // best: [n_trees][n] global row id -> local id of the relocated node
-    uint8_t* cmp;               // random: [n_trees][n] comparison bits of the candidate sweep, by position
-    int32_t* err;               // device error flag
+    int32_t* err;               // device [2]: error flag, max node count over the trees (atomicMax)
     int n, d, dp, n_trees, max_features, stack_cap, node_cap, side_words;
+    int salt;                   // per-launch value mixed into the leader-warp choice (f16_leader_warp)
 };
 
 struct f16_forest {
@@ -50,7 +50,8 @@ struct f16_forest {
     int64_t n_train;
     F16Node* nodes;      // device [n_trees][node_cap]
     int32_t* node_count; // device [n_trees]
-    int32_t* err;        // device
+    int32_t* err;        // device [2]: status code, largest node count of the trees
+    int max_nodes;       // host copy of err[1], filled by f16_forest_status
     cudaEvent_t ev0, ev1;   // around the tree-building kernel when profiling is on
     int has_ev;
 };

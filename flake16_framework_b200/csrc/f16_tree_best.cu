@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
     __shared__ int s_cntn[NW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lw = f16_leader_warp(P.salt);                 // the CTA's scalar-section warp
+    const int rtid = (tid - lw * 32) & (NT - 1);            // rotated: leader warp's lane 0 is 0
     const int t = blockIdx.x;
     const int n = P.n, d = P.d;
     const float* __restrict__ X = P.X;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (rtid == 0) {
         unsigned long long tot = s_part[0];
         for (int f = 0; f < F16_MAX_D; f++) { ds.features[f] = f; ds.const_feats[f] = 0; }
         ds.rng = P.rand_r_state[t];
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
 
     PH_T(1, 0);
     while (true) {
-        if (tid == 0) pop_node(c, stk);
+        if (rtid == 0) pop_node(c, stk);
         __syncthreads();
         if (c.done) break;
         const int nn = c.end - c.start;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     sdst[f * SB + p] = (e & ~F16_ID_MASK) | lid[f16_id(e)];
                 }
             }
-            if (tid == 0) { c.in_smem = 1; c.start = 0; c.end = nn; }
+            if (rtid == 0) { c.in_smem = 1; c.start = 0; c.end = nn; }
             __syncthreads();
             PH_T(1, 1);
         }
@@ -294,14 +296,14 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
 
         if (!c.leaf) {
             // ---- min / max of every not-yet-constant feature: ends of its sorted slice
-            if (tid < d && !((c.const_mask >> tid) & 1u)) {
-                const uint32_t* o = src + (size_t)tid * stride;
-                s_min[tid] = value(o[start], tid);
-                s_max[tid] = value(o[start + nn - 1], tid);
+            if (rtid < d && !((c.const_mask >> rtid) & 1u)) {
+                const uint32_t* o = src + (size_t)rtid * stride;
+                s_min[rtid] = value(o[start], rtid);
+                s_max[rtid] = value(o[start + nn - 1], rtid);
             }
             __syncthreads();
             // ---- Fisher-Yates feature draw (thread 0)
-            if (tid == 0) {
+            if (rtid == 0) {
                 const int max_features = P.max_features;
                 int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
                 const int n_known = c.n_const;
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 }
                 if (lane == 0) { s_bproxy[warp] = bp; s_bkey[warp] = bk; }
                 __syncthreads();
-                if (tid == 0) {
+                if (rtid == 0) {
                     double wp = s_bproxy[0]; unsigned long long wk = s_bkey[0];
                     for (int q = 1; q < NW; q++)
                         if (s_bproxy[q] > wp || (s_bproxy[q] == wp && s_bkey[q] < wk)) { wp = s_bproxy[q]; wk = s_bkey[q]; }
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 PH_T(1, sm ? 6 : 3);
             }
         }
-        if (tid == 0) finish_node(c, P, nodes, stk);
+        if (rtid == 0) finish_node(c, P, nodes, stk);
         __syncthreads();
         if (c.abort) break;
         if (c.split) {
@@ -429,13 +431,13 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 warp_partition(src + (size_t)f * stride, dst + (size_t)f * stride, start, nn, n_left, nside);
             }
             __syncthreads();
-            if (tid == 0) c.split = 0;
+            if (rtid == 0) c.split = 0;
             PH_T(1, sm ? 7 : 4);
         } else {
             PH_T(1, sm ? 9 : 8);
         }
     }
-    if (tid == 0) P.node_count[t] = c.node_count;
+    if (rtid == 0) { P.node_count[t] = c.node_count; atomicMax(P.err + 1, c.node_count); }
 }
 
 F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))

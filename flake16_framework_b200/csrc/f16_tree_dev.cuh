@@ -21,6 +21,23 @@
 #define F16_EPS 2.220446049250313e-16
 #define SSTK 40     // stack records cached in shared memory (deeper ones spill to global)
 
+// The scalar sections of a tree (pop, feature draw, node record) and the single-warp subtree regime
+// run on ONE warp of the CTA.  A warp's scheduler (SM sub-partition) is its index within the CTA
+// modulo 4, so if that warp were warp 0 in every CTA, the serial sections of all CTAs resident on
+// an SM would queue on sub-partition 0 while the other three idle.  The leader warp is therefore
+// drawn per CTA and per launch; `rtid` is the thread index rotated so that the leader warp's
+// lane 0 is 0 - role tests use rtid, data-parallel loops keep tid.
+#ifndef F16_ROT
+#define F16_ROT 1
+#endif
+__device__ __forceinline__ int f16_leader_warp(int salt) {
+#if F16_ROT
+    return (int)(((((uint32_t)blockIdx.x + (uint32_t)salt) * 2654435761u) >> 16) % (uint32_t)NW);
+#else
+    return 0;
+#endif
+}
+
 // ------------------------------------------------------------------ shared control block
 struct Ctl {
     int start, end, parent, c0, c1, n_const, is_left, depth;
@@ -213,7 +230,6 @@ static __device__ unsigned long long f16_phase_nodes[2][F16_NPH];
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
 int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);
-int f16_launch_build_random_w(const F16FitParams& P, cudaStream_t st);
 int f16_launch_build_best_rf(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_build_best_dt(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

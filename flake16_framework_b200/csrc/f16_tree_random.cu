@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     __shared__ uint8_t s_y[S];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lw = f16_leader_warp(P.salt);                 // the CTA's scalar / subtree warp
+    const int rtid = (tid - lw * 32) & (NT - 1);            // rotated: leader warp's lane 0 is 0
     const int t = blockIdx.x;
     const int n = P.n;
     const float* __restrict__ X = P.X;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     cnt = f16_warp_sum_u64(cnt);
     if (lane == 0) s_part[warp][0] = cnt;
     __syncthreads();
-    if (tid == 0) {
+    if (rtid == 0) {
         unsigned long long tot = 0;
         for (int q = 0; q < NW; q++) tot += s_part[q][0];
         for (int f = 0; f < F16_MAX_D; f++) { ds.features[f] = f; ds.const_feats[f] = 0; }
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
     PH_T(0, 0);
 
     while (true) {
-        if (tid == 0) pop_node(c, stk);
+        if (rtid == 0) pop_node(c, stk);
         __syncthreads();
         if (c.done) break;
         const int start = c.start, nn = c.end - c.start;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                     if (q == 0) { s_idx[c.depth & 1][i] = (uint16_t)i; s_y[i] = (uint8_t)f16_y(e); }
                 }
             }
-            if (tid == 0) {
+            if (rtid == 0) {
                 F16StackRec r;
                 r.start = 0; r.end = nn; r.parent = c.parent; r.c0 = c.c0; r.c1 = c.c1;
                 r.const_mask = c.const_mask; r.n_const = (int16_t)c.n_const; r.is_left = (uint8_t)c.is_left;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
             }
             __syncthreads();
             PH_T(0, 1);
-            if (warp == 0) subtree_warp_v2<DP, S>(c, ds, stk, P, nodes, s_col, s_idx, s_y);
+            if (warp == lw) subtree_warp_v2<DP, S>(c, ds, stk, P, nodes, s_col, s_idx, s_y);
             __syncthreads();
             PH_T(0, 5);
             if (c.abort) break;
@@ -161,16 +163,16 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                     for (int j = 0; j < 4; j++) { s_wmin[warp][lane * 4 + j] = mn[j]; s_wmax[warp][lane * 4 + j] = mx[j]; }
                 }
                 __syncthreads();
-                if (tid < DP) {
-                    float a = s_wmin[0][tid], b = s_wmax[0][tid];
+                if (rtid < DP) {
+                    float a = s_wmin[0][rtid], b = s_wmax[0][rtid];
 #pragma unroll
-                    for (int q2 = 1; q2 < NW; q2++) { a = fminf(a, s_wmin[q2][tid]); b = fmaxf(b, s_wmax[q2][tid]); }
-                    s_min[tid] = a; s_max[tid] = b;
+                    for (int q2 = 1; q2 < NW; q2++) { a = fminf(a, s_wmin[q2][rtid]); b = fmaxf(b, s_wmax[q2][rtid]); }
+                    s_min[rtid] = a; s_max[rtid] = b;
                 }
                 __syncthreads();
             }
             // ---- draw features + thresholds (thread 0; scalar xorshift stream)
-            if (tid == 0) {
+            if (rtid == 0) {
                 const int d = P.d, max_features = P.max_features;
                 int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
                 const int n_known = c.n_const;
@@ -237,15 +239,15 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                     acc += __shfl_xor_sync(F16_FULL, acc, 16);
                     if (lane < 4) s_part[warp][lane] = acc;
                     __syncthreads();
-                    if (tid < 4 && k0 + tid < ncand) {
+                    if (rtid < 4 && k0 + rtid < ncand) {
                         unsigned long long s = 0;
-                        for (int q2 = 0; q2 < NW; q2++) s += s_part[q2][tid];
-                        s_cnt[k0 + tid] = s;
+                        for (int q2 = 0; q2 < NW; q2++) s += s_part[q2][rtid];
+                        s_cnt[k0 + rtid] = s;
                     }
                     __syncthreads();
                 }
                 // ---- choose the best candidate (strict >, first wins)
-                if (tid == 0) {
+                if (rtid == 0) {
                     double best = -INFINITY; int bk = -1;
                     for (int k = 0; k < ncand; k++) {
                         int nl = (int)(uint32_t)s_cnt[k], l1 = (int)(s_cnt[k] >> 32), l0 = nl - l1;
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                 }
             }
         }
-        if (tid == 0) finish_node(c, P, nodes, stk);
+        if (rtid == 0) finish_node(c, P, nodes, stk);
         __syncthreads();
         PH_T(0, c.leaf ? 6 : 3);
         if (c.abort) break;
@@ -272,11 +274,11 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
             block_partition(src, dst, start, nn, c.n_left,
                             [&](uint32_t e, int) { return __ldg(X + (size_t)f16_id(e) * DP + bf) <= bthr; }, s_wcnt);
             __syncthreads();
-            if (tid == 0) c.split = 0;
+            if (rtid == 0) c.split = 0;
             PH_T(0, 4);
         }
     }
-    if (tid == 0) P.node_count[t] = c.node_count;
+    if (rtid == 0) { P.node_count[t] = c.node_count; atomicMax(P.err + 1, c.node_count); }
 }
 
 F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))

@@ -16,6 +16,11 @@ from . import _lib
 from ._lib import check
 
 KIND_DT, KIND_RF, KIND_ET = 0, 1, 2
+F16_ERR_OVERFLOW = -3
+
+
+class F16Overflow(_lib.F16Error):
+    """A device-side capacity was exceeded (node array of f16_forest_fit_cap, DFS stack, bootstrap weight)."""
 
 
 def _stream():
@@ -68,6 +73,14 @@ def gather_u8(y, idx):
     return out
 
 
+def gather_i32(v, idx):
+    L = _ready()
+    assert v.dtype == torch.int32 and idx.dtype == torch.int64
+    out = torch.empty((idx.shape[0],), dtype=torch.int32, device=v.device)
+    check(L.f16_gather_i32(_ptr(v), _ptr(idx), idx.shape[0], _ptr(out), _stream()))
+    return out
+
+
 def argsort_columns(Xrow, d):
     L = _ready()
     n = Xrow.shape[0]
@@ -115,7 +128,14 @@ class Forest:
 
     def status(self):
         """Synchronises the current stream; raises if the device-side fit failed."""
-        check(_lib.lib().f16_forest_status(self._h, _stream()))
+        rc = _lib.lib().f16_forest_status(self._h, _stream())
+        if rc == F16_ERR_OVERFLOW:
+            raise F16Overflow(_lib.lib().f16_last_error().decode())
+        check(rc)
+
+    def max_nodes(self):
+        """Largest node count of the forest's trees (valid after ``status``)."""
+        return int(_lib.lib().f16_forest_max_nodes(self._h))
 
     def node_counts(self):
         c = np.zeros(self.n_trees, dtype=np.int32)
@@ -157,7 +177,8 @@ def resolve_max_features(kind, d):
     return d if kind == KIND_DT else max(1, int(np.sqrt(d)))
 
 
-def forest_fit(Xrow, y, d, kind, n_estimators=100, seed=0, sorted_idx=None, max_features=None):
+def forest_fit(Xrow, y, d, kind, n_estimators=100, seed=0, sorted_idx=None, max_features=None, node_cap=0):
+    """``node_cap``: per-tree node capacity (0 = worst case 2n - 1); see f16_forest_fit_cap."""
     L = _ready()
     n = Xrow.shape[0]
     assert Xrow.dtype == torch.float32 and Xrow.shape[1] == padded_dim(d) and Xrow.is_contiguous()
@@ -167,8 +188,8 @@ def forest_fit(Xrow, y, d, kind, n_estimators=100, seed=0, sorted_idx=None, max_
     if max_features is None:
         max_features = resolve_max_features(kind, d)
     h = ctypes.c_void_p()
-    check(L.f16_forest_fit(_ptr(Xrow), _ptr(y), n, d, _ptr(sorted_idx), kind, n_estimators, max_features,
-                           seed, _stream(), ctypes.byref(h)))
+    check(L.f16_forest_fit_cap(_ptr(Xrow), _ptr(y), n, d, _ptr(sorted_idx), kind, n_estimators, max_features,
+                               seed, int(node_cap), _stream(), ctypes.byref(h)))
     return Forest(h, kind, d, n)
 
 

@@ -94,6 +94,7 @@ class _DeviceData:
             self.col_order[key] = seen[key[1:]]
         self.y = {k: torch.from_numpy(v.astype(np.uint8)).to(device) for k, v in gd.labels.items()}
         self.proj = torch.from_numpy(gd.proj_id).to(device)
+        self.caps = _NodeCaps()          # learnt node capacities persist across passes over this data
         self.fold_idx = {}
         for ft, tf in gd.folds.items():
             for i, (tr, te) in enumerate(hp.kfold_split(tf, gd.n_splits)):
@@ -111,8 +112,14 @@ class _DeviceData:
         return b
 
 
+# Balancings that share intermediate results stay in one work item: the k=4 neighbour table of the
+# training rows serves TomekLinks and ENN; the SMOTE'd set and its neighbour table serve SMOTE,
+# SMOTE ENN and SMOTE Tomek.
+BALANCING_GROUPS = (("None", "Tomek Links", "ENN"), ("SMOTE", "SMOTE ENN", "SMOTE Tomek"))
+
+
 def _unit_cost(gd, unit, wanted):
-    (ft, fs, pre), fold = unit
+    (ft, fs, pre), fold = unit[0], unit[1]
     d = gd.datasets[(ft, fs, pre)].shape[1]
     n = gd.datasets[(ft, fs, pre)].shape[0]
     cost = 0.0
@@ -123,15 +130,25 @@ def _unit_cost(gd, unit, wanted):
     return cost
 
 
-def plan_units(gd, configs, n_splits, world):
-    """(dataset, fold) units, what each must produce ({balancing: [models]}), and their
-    longest-processing-time-first assignment to ``world`` ranks (deterministic, so every rank
-    derives the same plan without communicating)."""
+def plan_units(gd, configs, n_splits, world, folds=None):
+    """Work items (dataset, fold, balancing group), what each must produce ({balancing: [models]}),
+    and their longest-processing-time-first assignment to ``world`` ranks (deterministic, so every
+    rank derives the same plan without communicating).  720 (dataset, balancing, fold) resamples
+    of the full grid -> 240 items of <= 9 fits.  ``folds`` restricts the plan to those fold indices
+    (bench.py's parity check runs fold 0 only)."""
     wanted_by_ds = {}
     for c in configs:
         wanted_by_ds.setdefault(tuple(c[:3]), {}).setdefault(c[3], []).append(c[4])
-    units = [(ds, f) for ds in wanted_by_ds for f in range(n_splits)]
-    cost = {u: _unit_cost(gd, u, wanted_by_ds[u[0]]) for u in units}
+    wanted, units = {}, []
+    for ds, w in wanted_by_ds.items():
+        for g, group in enumerate(BALANCING_GROUPS):
+            wg = {bal: w[bal] for bal in group if bal in w}
+            if not wg:
+                continue
+            for f in (range(n_splits) if folds is None else folds):
+                units.append((ds, f, g))
+                wanted[(ds, f, g)] = wg
+    cost = {u: _unit_cost(gd, u, wanted[u]) for u in units}
     units.sort(key=lambda u: (-cost[u], u))
     load = [0.0] * world
     shards = [[] for _ in range(world)]
@@ -139,7 +156,7 @@ def plan_units(gd, configs, n_splits, world):
         r = int(np.argmin(load))
         load[r] += cost[u]
         shards[r].append(u)
-    return wanted_by_ds, shards
+    return wanted, shards
 
 
 def _minority_clean_mask(counts, strategy):
@@ -149,9 +166,30 @@ def _minority_clean_mask(counts, strategy):
     return 0b11 & ~(1 << minority)
 
 
-def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers, model_streams):
-    """One (dataset, fold): stage, resample per balancing, fit/predict/count per model."""
-    ds_key, fold = unit
+class _NodeCaps:
+    """Per-tree node capacity for f16_forest_fit_cap, learnt from the fits already settled: the
+    worst case 2n - 1 costs 32 B x (2n - 1) per tree (1.1 GB per 100-tree forest at 178 k rows,
+    57 GB for 500 trees at 1.8 M), real trees of this path hold 0.03 n - 0.3 n nodes.  Key = (model,
+    d, resampled?); capacity = 1.5 x the largest nodes / n ratio seen + 1024.  The first fit of a
+    key uses the worst case; if a later fit overflows its capacity (F16_ERR_OVERFLOW from
+    f16_forest_status) run_grid repeats the whole pass with capacities disabled."""
+
+    def __init__(self, enabled=True):
+        self.ratio, self.lock, self.enabled = {}, threading.Lock(), enabled
+
+    def cap(self, key, n):
+        with self.lock:
+            r = self.ratio.get(key) if self.enabled else None
+        return 0 if r is None else min(2 * n - 1, int(1.5 * r * n) + 1024)
+
+    def update(self, key, n, max_nodes):
+        with self.lock:
+            self.ratio[key] = max(self.ratio.get(key, 0.0), max_nodes / float(n))
+
+
+def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers, model_streams, caps):
+    """One (dataset, fold, balancing group): stage, resample per balancing, fit/predict/count per model."""
+    ds_key, fold = unit[0], unit[1]
     ft = ds_key[0]
     X64 = dd.X[ds_key]
     d = X64.shape[1]
@@ -159,7 +197,7 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
     tr_idx, te_idx, counts, pos_in_tr, neg_in_tr = dd.fold_idx[(ft, fold)]
     Xte = ops.rows_f32(X64, te_idx)
     yte = ops.gather_u8(y_all, te_idx)
-    pte = dd.proj[te_idx]
+    pte = ops.gather_i32(dd.proj, te_idx)
     ytr = ops.gather_u8(y_all, tr_idx)
     need64 = any(b != "None" for b in wanted)
     Xtr64 = ops.gather_rows_f64(X64, tr_idx) if need64 else None
@@ -230,13 +268,16 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
             with torch.cuda.stream(side):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
-                forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx)
+                cap_key = (model, d, bal != "None")
+                n_fit = Xrow.shape[0]
+                node_cap = caps.cap(cap_key, n_fit)
+                forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx, node_cap=node_cap)
                 e1.record()
                 pred = forest.predict(Xte)
                 e2.record()
                 ops.confusion(yte, pred, pte, gd.n_proj, counts_all[ci])
                 keep.append(pred)
-            timers.append((ci, e0, e1, e2, forest))
+            timers.append((ci, e0, e1, e2, forest, cap_key, n_fit))
     # completion markers instead of a drain: the worker goes on to its next unit and settles this
     # one (status, timings, frees) later, so its streams never run dry between units
     events = []
@@ -261,7 +302,7 @@ def prepare(parsed, configs=None, device=None, n_splits=10):
 
 
 def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFAULT_WORKERS, device=None,
-             rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None):
+             rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None, folds=None):
     """Computes the scores dict for ``configs`` (default: the full 216 grid).
 
     Returns {config_keys: [t_train / n_splits, t_test / n_splits, scores, scores_total]} - the
@@ -273,75 +314,90 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFA
     if stats is not None:
         stats["h2d_bytes"] = dd.h2d_bytes()
     cfg_index = {c: i for i, c in enumerate(configs)}
-    counts_all = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
-    times = np.zeros((len(configs), 2), dtype=np.float64)
-
-    wanted_by_ds, shards = plan_units(gd, configs, n_splits, world)
+    wanted, shards = plan_units(gd, configs, n_splits, world, folds)
     mine = shards[rank]
+    n_lanes = int(os.environ.get("F16_LANES", str(DEFAULT_LANES)))
 
-    q = queue.Queue()
-    for u in mine:
-        q.put(u)
-    errors = []
-    lock = threading.Lock()
-    done = [0]
+    def one_pass(caps):
+        """All of this rank's work items once; returns (counts, times, a fit overflowed its node capacity)."""
+        counts_all = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
+        # the zero fill runs on the caller's stream; the workers' non-blocking streams must not
+        # start accumulating before it has completed
+        torch.cuda.current_stream(device).synchronize()
+        times = np.zeros((len(configs), 2), dtype=np.float64)
+        q = queue.Queue()
+        for u in mine:
+            q.put(u)
+        errors, overflow = [], [False]
+        lock = threading.Lock()
+        done = [0]
 
-    def worker():
-        torch.cuda.set_device(device)
-        stream = torch.cuda.Stream(device=device)
-        # several forests of one unit in flight: n_lanes side streams per forest model, 2 for the tree
-        n_lanes = int(os.environ.get("F16_LANES", str(DEFAULT_LANES)))
-        model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
-                         for m in MODELS}
-        util = torch.cuda.Stream(device=device)     # status reads / frees of settled units
-        pending = []
+        def worker():
+            torch.cuda.set_device(device)
+            stream = torch.cuda.Stream(device=device)
+            # several forests of one item in flight: n_lanes side streams per forest model, 2 for the tree
+            model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
+                             for m in MODELS}
+            util = torch.cuda.Stream(device=device)     # status reads / frees of settled items
+            pending = []
 
-        def settle(item):
-            events, keep, timers = item
-            for e in events:
-                e.synchronize()
-            with torch.cuda.stream(util):
-                for ci, e0, e1, e2, forest in timers:
-                    forest.status()
-                    with lock:
-                        times[ci, 0] += e0.elapsed_time(e1) * 1e-3
-                        times[ci, 1] += e1.elapsed_time(e2) * 1e-3
-                    forest.free()
-            keep.clear()
-            with lock:
-                done[0] += 1
-                if progress:
-                    progress(done[0], len(mine))
+            def settle(item):
+                events, keep, timers = item
+                for e in events:
+                    e.synchronize()
+                with torch.cuda.stream(util):
+                    for ci, e0, e1, e2, forest, cap_key, n_fit in timers:
+                        try:
+                            forest.status()
+                            caps.update(cap_key, n_fit, forest.max_nodes())
+                        except ops.F16Overflow:
+                            overflow[0] = True
+                        with lock:
+                            times[ci, 0] += e0.elapsed_time(e1) * 1e-3
+                            times[ci, 1] += e1.elapsed_time(e2) * 1e-3
+                        forest.free()
+                keep.clear()
+                with lock:
+                    done[0] += 1
+                    if progress:
+                        progress(done[0], len(mine))
 
-        try:
-            with torch.cuda.stream(stream):
-                while True:
-                    try:
-                        u = q.get_nowait()
-                    except queue.Empty:
-                        break
-                    timers = []
-                    with ops.column_order(dd.col_order[u[0]]):
-                        events, keep = _run_unit(gd, dd, u, wanted_by_ds[u[0]], cfg_index, counts_all, n_estimators,
-                                                 timers, model_streams)
-                    pending.append((events, keep, timers))
-                    if len(pending) > 1:            # one unit in flight behind the current one
+            try:
+                with torch.cuda.stream(stream):
+                    while True:
+                        try:
+                            u = q.get_nowait()
+                        except queue.Empty:
+                            break
+                        timers = []
+                        with ops.column_order(dd.col_order[u[0]]):
+                            events, keep = _run_unit(gd, dd, u, wanted[u], cfg_index, counts_all, n_estimators,
+                                                     timers, model_streams, caps)
+                        pending.append((events, keep, timers))
+                        if len(pending) > 1:            # one item in flight behind the current one
+                            settle(pending.pop(0))
+                    while pending:
                         settle(pending.pop(0))
-                while pending:
-                    settle(pending.pop(0))
-        except Exception as ex:  # propagate to the caller
-            with lock:
-                errors.append(ex)
+            except Exception as ex:  # propagate to the caller
+                with lock:
+                    errors.append(ex)
 
-    n_thr = max(1, min(n_streams, len(mine)))
-    threads = [threading.Thread(target=worker, daemon=True) for _ in range(n_thr)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
-    torch.cuda.synchronize(device)
+        n_thr = max(1, min(n_streams, len(mine)))
+        threads = [threading.Thread(target=worker, daemon=True) for _ in range(n_thr)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        torch.cuda.synchronize(device)
+        return counts_all, times, overflow[0]
+
+    counts_all, times, overflowed = one_pass(dd.caps)
+    if overflowed:          # a tree outgrew its learnt node capacity: redo the pass with the worst case
+        counts_all, times, overflowed = one_pass(_NodeCaps(enabled=False))
+        if overflowed:
+            raise ops.F16Overflow("a tree exceeded the worst-case node capacity 2n - 1 (corrupt input?)")
 
     if world > 1:
         import torch.distributed as dist

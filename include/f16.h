@@ -56,6 +56,8 @@ int f16_gather_rows_f32(const double* X_dev, int32_t d, const int64_t* idx_dev, 
 int f16_gather_rows_f64(const double* X_dev, int32_t d, const int64_t* idx_dev, int64_t n_out,
                         double* out_dev, void* stream);
 int f16_gather_u8(const uint8_t* y_dev, const int64_t* idx_dev, int64_t n_out, uint8_t* out_dev, void* stream);
+/* projects[test]  (experiment.py:460,477): project id of every test row. */
+int f16_gather_i32(const int32_t* v_dev, const int64_t* idx_dev, int64_t n_out, int32_t* out_dev, void* stream);
 
 /* ---- tree ensembles -------------------------------------------------------------------
  * Per-column argsort of a float32 row matrix ([n][dp]); sorted_idx_dev: int32 [d][n].
@@ -78,11 +80,20 @@ int f16_bootstrap_counts(const uint32_t* tree_seed_host, int32_t n_trees, int64_
 int f16_forest_fit(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
                    const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
                    int32_t max_features, uint32_t seed, void* stream, f16_forest** out);
+/* The same fit with an explicit per-tree node capacity (0 = the worst case 2n - 1).  A tree that
+ * outgrows the capacity makes f16_forest_status return F16_ERR_OVERFLOW; nothing is written out
+ * of bounds.  The grid engine passes capacities measured on earlier fits (real trees of this path
+ * hold 0.03 n - 0.15 n nodes) and refits with 0 on overflow. */
+int f16_forest_fit_cap(const float* X_dev, const uint8_t* y_dev, int64_t n, int32_t d,
+                       const int32_t* sorted_idx_dev, int32_t kind, int32_t n_estimators,
+                       int32_t max_features, uint32_t seed, int64_t node_cap, void* stream, f16_forest** out);
 /* model.predict(features_test)  (experiment.py:473): pred_dev uint8 [n] class index. */
 int f16_forest_predict(const f16_forest* forest, const float* X_dev, int64_t n, uint8_t* pred_dev, void* stream);
 /* Synchronises the stream; returns the device-side status of the fit (0 = ok). */
 int f16_forest_status(const f16_forest* forest, void* stream);
 int f16_forest_n_trees(const f16_forest* forest);
+/* Largest node count among the forest's trees, as read by the last f16_forest_status (0 before). */
+int f16_forest_max_nodes(const f16_forest* forest);
 /* Synchronises. counts_host: int32 [n_trees]. */
 int f16_forest_node_counts(const f16_forest* forest, int32_t* counts_host, void* stream);
 /* Synchronises. One tree in sklearn's tree_ layout (children_left/right, feature, threshold,
@@ -97,7 +108,7 @@ void f16_forest_free(f16_forest* forest, void* stream);
  * [nq][k], ordered by (distance, index).  k <= 8, d <= 16.  col_order (HOST pointer, d ints, or
  * NULL) is the order in which coordinates are accumulated: highest-variance columns first make
  * the partial-distance early exit effective.  prefix_test selects the search strategy: 0 plain
- * float64 filter, 1 early exit on the two leading columns (raw features), 2 float32 filter,
+ * float64 filter, 1 early exit on the two leading columns (raw features), 2 retired (= 0),
  * 3 tensor-core candidate filter (float16 x 3 split, mma.sync) followed by exact float64
  * selection - for centred data of moderate range (StandardScaler / PCA outputs); data that does
  * not fit float16 is detected on the device and searched exhaustively; 6 sweep over the rows sorted

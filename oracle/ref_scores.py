@@ -92,9 +92,12 @@ def get_prf(fp, fn, tp):                                             # experimen
     return p, r, f
 
 
-def get_scores(config_keys, tests_file=None, grid=None, n_splits=10, max_folds=None):
+def get_scores(config_keys, tests_file=None, grid=None, n_splits=10, max_folds=None, timing=None):
     """experiment.py:446-490.  ``max_folds`` (not in the reference) stops after that many
-    folds - used only to bound the CPU-baseline sample in bench.py."""
+    folds - used only to bound the CPU-baseline sample in bench.py; ``timing`` (a dict, not in
+    the reference either) receives the seconds spent before the fold loop (JSON parse +
+    preprocessing, ``setup_s``) and inside it (``folds_s``) for that bench leg's extrapolation."""
+    t_enter = time.time()
     grid = grid or CONFIG_GRID
     config_vals = [grid[i][k] for i, k in enumerate(config_keys)]
     flaky_label, feature_set, preprocessing, balancing, model = config_vals
@@ -106,6 +109,7 @@ def get_scores(config_keys, tests_file=None, grid=None, n_splits=10, max_folds=N
 
     t_train = t_test = 0
     scores, scores_total = {proj: [0] * 6 for proj in projects}, [0] * 6
+    t_loop = time.time()
 
     for i, (train, test) in enumerate(fold.split(features, labels)):
         if max_folds is not None and i >= max_folds:
@@ -134,6 +138,9 @@ def get_scores(config_keys, tests_file=None, grid=None, n_splits=10, max_folds=N
             scores[projects_test[j]][k] += 1
             scores_total[k] += 1
 
+    if timing is not None:
+        timing["setup_s"] = t_loop - t_enter
+        timing["folds_s"] = time.time() - t_loop
     for scores_proj in [*scores.values(), scores_total]:
         scores_proj[3:] = get_prf(*scores_proj[:3])
 
@@ -156,6 +163,30 @@ def _worker(args):
             return get_scores(config_keys, tests_file, grid, n_splits, max_folds)
     except ImportError:
         return get_scores(config_keys, tests_file, grid, n_splits, max_folds)
+
+
+def _timed_worker(args):
+    """get_scores on ``max_folds`` folds + its setup / fold-loop seconds (bench.py's CPU arm)."""
+    config_keys, tests_file, n_splits, max_folds, n_estimators = args
+    grid = make_config_grid(n_estimators)
+    timing = {}
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            _, (_, _, _, scores, total) = get_scores(config_keys, tests_file, grid, n_splits, max_folds, timing)
+    except ImportError:
+        _, (_, _, _, scores, total) = get_scores(config_keys, tests_file, grid, n_splits, max_folds, timing)
+    counts = {str(p): [int(v) for v in s[:3]] for p, s in scores.items()}
+    return tuple(config_keys), timing, counts, [int(v) for v in total[:3]]
+
+
+def run_configs_timed(configs, tests_file, processes, n_splits=10, max_folds=1, n_estimators=100):
+    """One process per task (maxtasksperchild=1: a worker never carries a warm cache from one
+    task to the next, like distinct Pool workers in the reference)."""
+    from multiprocessing import Pool
+    args = [(c, tests_file, n_splits, max_folds, n_estimators) for c in configs]
+    with Pool(processes=processes, maxtasksperchild=1) as pool:
+        return list(pool.imap_unordered(_timed_worker, args, chunksize=1))
 
 
 def run_configs(configs, tests_file, processes=None, n_splits=10, max_folds=None,

@@ -148,8 +148,9 @@ def _gloo_worker(rank, world, port, q):
     wanted, shards = S.plan_units(gd, configs, 10, world)
     cfg_index = {c: i for i, c in enumerate(configs)}
     counts = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64)
-    for (ds, fold) in shards[rank]:                      # fake, deterministic per-(unit, config) counts
-        for bal, models in wanted[ds].items():
+    for u in shards[rank]:                               # fake, deterministic per-(item, config) counts
+        ds, fold = u[0], u[1]
+        for bal, models in wanted[u].items():
             for m in models:
                 ci = cfg_index[ds + (bal, m)]
                 counts[ci] += (fold + 1) * (ci + 1)
@@ -172,7 +173,7 @@ def test_world_size_2_sharding_and_reduce():
     counts, sizes = q.get(timeout=120)
     for p in procs:
         p.join(60)
-    assert sum(sizes) == 120 and abs(sizes[0] - sizes[1]) <= 30
+    assert sum(sizes) == 240 and abs(sizes[0] - sizes[1]) <= 60
     expect = np.array([sum(f + 1 for f in range(10)) * (ci + 1) for ci in range(216)])
     assert np.array_equal(counts[:, 0, 0], expect)
 
@@ -266,9 +267,10 @@ def test_small_modulus_table_in_common_header():
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_unit_plan_is_a_balanced_partition(world):
-    """(dataset, fold) units are assigned longest-processing-time-first; every rank
-    derives the same plan without communicating, every unit is owned exactly once and the modelled
-    loads of the ranks stay within 10 % of each other up to 8 GPUs."""
+    """(dataset, fold, balancing group) work items are assigned
+    longest-processing-time-first; every rank derives the same plan without communicating, every
+    item is owned exactly once, together they cover the 720 (dataset, balancing, fold) resamples,
+    and the modelled loads of the ranks stay within 5 % of each other up to 8 GPUs."""
     from flake16_framework_b200 import hostprep as hp, scores as S, synth
     parsed = hp.tests_to_arrays(synth.make_tests_dict(3000, 16))
     cfgs = S.all_config_keys()
@@ -277,6 +279,10 @@ def test_unit_plan_is_a_balanced_partition(world):
     wanted2, shards2 = S.plan_units(gd, cfgs, 10, world)
     assert shards == shards2                                    # deterministic
     flat = [u for sh in shards for u in sh]
-    assert len(flat) == 120 and len(set(flat)) == 120
-    loads = [sum(S._unit_cost(gd, u, wanted[u[0]]) for u in sh) for sh in shards]
-    assert max(loads) <= 1.10 * (sum(loads) / world)
+    assert len(flat) == 240 and len(set(flat)) == 240
+    assert sum(len(wanted[u]) for u in flat) == 720 and sum(len(m) for u in flat for m in wanted[u].values()) == 2160
+    loads = [sum(S._unit_cost(gd, u, wanted[u]) for u in sh) for sh in shards]
+    assert max(loads) <= 1.05 * (sum(loads) / world)
+    # bench.py's parity check plans a single fold
+    _, one = S.plan_units(gd, cfgs, 10, 1, folds=[0])
+    assert len(one[0]) == 24 and all(u[1] == 0 for u in one[0])
