@@ -51,12 +51,19 @@ def parse_args():
     ap.add_argument("--n-estimators", type=int, default=100)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("F16_STREAMS", "4")))
     ap.add_argument("--configs", default="grid216",
-                    help="grid216 | slice (1 dataset, 18 configs) | config5 (BASELINE configs[4]: the 12 datasets x "
-                         "SMOTE ENN x Extra Trees; use with --n-tests 1000000 --n-estimators 500)")
+                    help="grid216 | slice (1 dataset, 18 configs) | config2 (BASELINE configs[1]: RandomForest, Flake16, no "
+                         "balancing; use with --cv group --n-splits 5) | config3 (configs[2]: ExtraTrees + SMOTE, Flake16, "
+                         "Scaling, NOD + OD) | config5 (configs[4]: the 12 datasets x SMOTE ENN x Extra Trees; use with "
+                         "--n-tests 1000000 --n-estimators 500)")
+    ap.add_argument("--cv", default="stratified", choices=["stratified", "group"],
+                    help="stratified: the reference's StratifiedKFold; group: StratifiedGroupKFold over the projects (configs[1])")
+    ap.add_argument("--n-splits", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probes", action="store_true", help="skip the single-kernel roofline probes")
+    ap.add_argument("--cpu-sample-out", default=None, help=argparse.SUPPRESS)     # internal: run the CPU sample, dump JSON
+    ap.add_argument("--cpu-sample-tests", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-budget-s", type=float, default=240.0,
                     help="reference arm: stop repeating the CPU sample when the next repetition would pass this budget")
     return ap.parse_args()
@@ -65,6 +72,10 @@ def parse_args():
 def select_configs(all_keys, which):
     if which == "slice":
         return [c for c in all_keys if c[:3] == ("NOD", "Flake16", "Scaling")]
+    if which == "config2":
+        return [c for c in all_keys if c == ("NOD", "Flake16", "None", "None", "Random Forest")]
+    if which == "config3":
+        return [c for c in all_keys if c[1:] == ("Flake16", "Scaling", "SMOTE", "Extra Trees")]
     if which == "config5":
         return [c for c in all_keys if c[3] == "SMOTE ENN" and c[4] == "Extra Trees"]
     return list(all_keys)
@@ -73,11 +84,14 @@ def select_configs(all_keys, which):
 def workload_config(args):
     names = {"grid216": "full scores grid: 216 configs x 10-fold CV, %d-tree forests" % args.n_estimators,
              "slice": "grid slice NOD/Flake16/Scaling: 18 configs x 10-fold CV, %d-tree forests" % args.n_estimators,
+             "config2": "BASELINE configs[1]: RandomForest n_estimators=%d, Flake16, no preprocessing / balancing, NOD" % args.n_estimators,
+             "config3": "BASELINE configs[2]: ExtraTrees n_estimators=%d + SMOTE, Flake16, Scaling, NOD + OD" % args.n_estimators,
              "config5": "BASELINE configs[4]: ExtraTrees n_estimators=%d + SMOTE-ENN on the 12 (flaky type, feature set, "
                         "preprocessing) datasets x 10-fold CV" % args.n_estimators}
-    n_cfg = {"grid216": 216, "slice": 18, "config5": 12}[args.configs]
-    return {"workload": "%s, synthetic tests.json %d tests x 16 features (seed 16)" % (names[args.configs], args.n_tests),
-            "n_tests": args.n_tests, "n_configs": n_cfg, "n_splits": 10,
+    n_cfg = {"grid216": 216, "slice": 18, "config2": 1, "config3": 2, "config5": 12}[args.configs]
+    return {"workload": "%s, synthetic tests.json %d tests x 16 features (seed 16)" % (names[args.configs].replace("10-fold", "%d-fold" % args.n_splits), args.n_tests),
+            "n_tests": args.n_tests, "n_configs": n_cfg, "n_splits": args.n_splits,
+            "cv": "StratifiedKFold(shuffle, random_state=0)" if args.cv == "stratified" else "StratifiedGroupKFold(groups=projects, shuffle, random_state=0)",
             "n_estimators": args.n_estimators, "parallelism": "grid-sharded x%d" % args.gpus,
             "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -144,6 +158,20 @@ def run_cpu_sample(tests_file, n_estimators=100):
     t0 = time.perf_counter()
     res = R.run_configs_timed(tasks, tests_file, workers, n_splits=10, max_folds=1, n_estimators=n_estimators)
     return res, time.perf_counter() - t0, workers
+
+
+def cpu_sample_subprocess(args, tests_file, out_file):
+    """The CPU sample in its own interpreter (no CUDA context, clean fork pool), started while the GPU
+    arm prepares and warms up - untimed work on both sides; it is joined BEFORE the timed region."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-out", out_file, "--cpu-sample-tests", tests_file,
+           "--n-estimators", str(args.n_estimators)]
+    return subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
+def cpu_sample_worker_main(args):
+    res, wall, workers = run_cpu_sample(args.cpu_sample_tests, args.n_estimators)
+    with open(args.cpu_sample_out, "w") as fd:
+        json.dump({"results": [[list(k), t, c, tot] for k, t, c, tot in res], "wall": wall, "workers": workers}, fd)
 
 
 def cpu_grid_estimate(results):
@@ -345,7 +373,12 @@ def ours_arm(args):
     synth.make_tests_json(tests_file, args.n_tests, 16)          # every rank: same seeded table
     parsed = hp.parse_tests(tests_file)
     configs = select_configs(S.all_config_keys(), args.configs)
-    prepared = S.prepare(parsed, configs, dev)
+    with_cpu = (world == 1 and not args.no_cpu_baseline and args.configs == "grid216" and args.cv == "stratified"
+                and args.n_splits == 10)
+    cpu_proc, cpu_out = None, os.path.join(tmp, "cpu_sample.json")
+    if with_cpu:
+        cpu_proc = cpu_sample_subprocess(args, tests_file, cpu_out)
+    prepared = S.prepare(parsed, configs, dev, args.n_splits, args.cv)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -356,11 +389,17 @@ def ours_arm(args):
             torch.cuda.synchronize(dev)
 
     def one_step():
-        return S.run_grid(parsed, configs, n_streams=args.streams, device=dev, rank=rank, world=world,
-                          n_estimators=args.n_estimators, prepared=prepared, return_counts=True)
+        return S.run_grid(parsed, configs, n_splits=args.n_splits, n_streams=args.streams, device=dev, rank=rank,
+                          world=world, n_estimators=args.n_estimators, prepared=prepared, return_counts=True)
 
     for _ in range(args.warmup):
         one_step()
+    cpu_sample = None
+    if cpu_proc is not None:            # the CPU sample must be over before anything is timed
+        _, err = cpu_proc.communicate()
+        if cpu_proc.returncode != 0:
+            raise RuntimeError("CPU sample failed:\n" + err.decode()[-2000:])
+        cpu_sample = json.load(open(cpu_out))
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -400,8 +439,10 @@ def ours_arm(args):
     e2e = None
     if not args.no_e2e:
         scores_file = os.path.join(tmp, "scores.pkl")
-        kw = dict(n_streams=args.streams, configs=configs, n_estimators=args.n_estimators)
+        kw = dict(n_streams=args.streams, configs=configs, n_estimators=args.n_estimators, n_splits=args.n_splits, cv=args.cv)
         e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        if total_ms / args.steps > 15e3:        # long steps: one end-to-end pass is enough (it differs from `value` by < 5 %)
+            e2e_steps = 1
         barrier()
         t0 = time.perf_counter()
         stats = None
@@ -426,7 +467,7 @@ def ours_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 criterion / f32 features / int counts",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(ln.item()),
-            "trees_per_s": (n_forest_cfg * trees_per_fit + n_dt_cfg) * 10 * args.steps / (total_ms * 1e-3),
+            "trees_per_s": (n_forest_cfg * trees_per_fit + n_dt_cfg) * args.n_splits * args.steps / (total_ms * 1e-3),
             "device_memory_in_use_bytes": int(peak_mem)}
     rc = 0
     if world == 1:
@@ -434,11 +475,14 @@ def ours_arm(args):
             line["roofline"] = tree_roofline_probe(parsed, L, "RF")
             line["roofline_et"] = tree_roofline_probe(parsed, L, "ET")
             line["roofline_knn"] = knn_roofline_probe(parsed)
-        if not args.no_cpu_baseline:
-            res, wall, workers = run_cpu_sample(tests_file, args.n_estimators)
+        if cpu_sample is not None:
+            res = [(tuple(k), t, c, tot) for k, t, c, tot in cpu_sample["results"]]
+            wall, workers = cpu_sample["wall"], cpu_sample["workers"]
             est = cpu_grid_estimate(res)
             line["cpu_baseline"] = {"value": est["value"], "unit": UNIT, "cores": workers, "kind": "port",
-                                    "sample": cpu_sample_desc(args.n_tests, args.n_estimators, workers) + " (%.0f s)" % wall,
+                                    "sample": cpu_sample_desc(args.n_tests, args.n_estimators, workers) +
+                                              " (%.0f s; run in a separate process during this arm's untimed preparation "
+                                              "and warm-up, finished before the timed region)" % wall,
                                     "host_cores": os.cpu_count(), "estimate": est}
             line["parity_check"] = parity_check(res, S, parsed, dev, args.streams, args.n_estimators)
             if not line["parity_check"]["identical"]:
@@ -450,6 +494,9 @@ def ours_arm(args):
 if __name__ == "__main__":
     a = parse_args()
     rc = 0
+    if a.cpu_sample_out:
+        cpu_sample_worker_main(a)
+        sys.exit(0)
     if a.impl == "reference":
         reference_arm(a)
     else:

@@ -5,6 +5,7 @@ stage (reference experiment.py:693-714 dispatches setup|container|run|tests|scor
 
     python experiment.py scores        # reads ./tests.json, writes ./scores.pkl
     python experiment.py tests         # reads ./data/, writes ./tests.json (the step before; host only)
+    python experiment.py shap          # reads ./tests.json, writes ./shap.pkl (the step after: TreeSHAP on the GPU)
 
 ``scores`` keeps the reference's file names (experiment.py:34-35) and pickle schema
 (experiment.py:488-490,498-501) but runs on B200 GPUs through libf16_b200.so.  Under
@@ -13,7 +14,9 @@ and the integer counts are all-reduced over NCCL; rank 0 writes the pickle.
 
 ``tests`` is the collation step that produces the hot path's input; it is
 host-side bookkeeping with the reference's function names (flake16_framework_b200/collate.py).
-The other reference commands (data collection in Docker, SHAP, LaTeX figures) are
+``shap`` (row N3) explains the reference's two configurations (experiment.py:520-530) with
+path-dependent TreeSHAP over the forests fitted on the device.
+The other reference commands (data collection in Docker, LaTeX figures) are
 outside this repo's scope and raise the same ``ValueError`` the
 reference raises for an unrecognised command (experiment.py:712-714).
 
@@ -57,6 +60,9 @@ def main(argv):
         write_scores()
     elif command == "tests" and not args:
         write_tests()
+    elif command == "shap" and not args:
+        from flake16_framework_b200 import explain
+        explain.write_shap(TESTS_FILE, explain.SHAP_FILE)
     elif command == "synth" and args:
         from flake16_framework_b200 import synth
         synth.make_tests_json(TESTS_FILE, int(args[0]), int(args[1]) if len(args) > 1 else 16)

@@ -33,6 +33,8 @@ def _sources(tune):
                                       "-DF16_MINB=%d" % t["RF_MINB"], "-DF16_WITH_BOOTSTRAP"] + x),
         ("f16_tree_best.cu", "_dt", ["-fmad=false", "-DF16_VARIANT=_dt", "-DNT=%d" % t["DT_NT"],
                                       "-DF16_MINB=%d" % t["DT_MINB"]] + x),
+        ("f16_shap.cu", "", []),
+        ("f16_stats.cu", "", []),
         ("f16_misc.cu", "", ["-fmad=false"]),
         ("f16_sort.cu", "", []),
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
@@ -114,6 +116,8 @@ SIGNATURES = {
     "f16_forest_node_counts": ([c_void_p, c_void_p, c_void_p], c_int),
     "f16_forest_export": ([c_void_p, c_int32, c_int64] + [c_void_p] * 8 + [c_void_p], c_int),
     "f16_forest_free": ([c_void_p, c_void_p], None),
+    "f16_forest_shap": ([c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
+    "f16_spearman": ([c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
     "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p], c_int),
     "f16_knn_tc_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),
     "f16_knn_umma_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) k_predict_walk(const F16Node* __restrict_
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const F16Node* tn = nodes + (size_t)blockIdx.y * node_cap;
-    const int nc = node_count[blockIdx.y];
+    const int nc = min(node_count[blockIdx.y], node_cap);     // an aborted fit counts the node it could not store
     const float* row = X + (size_t)i * DP;
     int id = 0;
     // a complete tree never leaves [0, nc) and is at most F16_STACK_CAP deep; a tree whose fit was

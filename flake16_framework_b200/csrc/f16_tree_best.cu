@@ -88,6 +88,9 @@ int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t
 #endif
 
 // ------------------------------------------------------------------ best splitter
+#ifndef F16_SPLIT_SCAN
+#define F16_SPLIT_SCAN 1     // two warps per evaluated feature when the CTA has them (see the candidate scan)
+#endif
 #define k_build_best F16_CAT(k_build_best, F16_VARIANT)
 struct BestCand {
     double proxy;
@@ -335,50 +338,106 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             __syncthreads();
             PH_T(1, sm ? 5 : 2);
             n_eval = c.ncand;
-            // ---- candidate scan: warp w owns evaluated features w, w+NW, ...
+            // ---- candidate scan.  A warp owns an evaluated feature; when the CTA has at least two
+            //      warps per evaluated feature (RandomForest: max_features = 4, 8 warps) the slice is
+            //      split in two: the even warp walks the first half upwards with LEFT prefix sums, the
+            //      odd warp walks the second half downwards with RIGHT suffix sums (left = node total
+            //      - right: the class sums are integers, so this is exact) - every warp of the CTA
+            //      works and no pre-pass is needed.  Ties are broken by the key (visit order, position).
             BestCand best;
             best.proxy = -INFINITY; best.key = ~0ull; best.v_prev = 0.f; best.v = 0.f; best.l0 = 0; best.l1 = 0;
             const int t0 = c.c0, t1 = c.c1;
-            for (int k = warp; k < n_eval; k += NW) {
+            const bool split_scan = F16_SPLIT_SCAN && (2 * n_eval <= NW);
+            const int n_scan = split_scan ? 2 * n_eval : n_eval;
+            for (int wk = warp; wk < n_scan; wk += NW) {
+                const int k = split_scan ? (wk >> 1) : wk;
+                const bool rev = split_scan && (wk & 1);
+                const int h = split_scan ? (nn + 1) / 2 : nn;   // upwards: positions [1, h); downwards: [h, nn)
                 const int f = s_eval_f[k];
                 const uint32_t* o = src + (size_t)f * stride + start;
                 unsigned long long carry = 0;
-                float prev_last = 0.f;
-                // 4 consecutive entries per lane: all 8 loads of a round are in flight together,
-                // one warp scan per 128 entries
-                for (int base = 0; base < nn; base += 128) {
-                    const int p0 = base + lane * 4;
-                    uint32_t e[4]; float v[4]; unsigned long long my[4];
+                if (!rev) {
+                    float prev_last = 0.f;
+                    // 4 consecutive entries per lane: all 8 loads of a round are in flight together,
+                    // one warp scan per 128 entries
+                    for (int base = 0; base < h; base += 128) {
+                        const int p0 = base + lane * 4;
+                        uint32_t e[4]; float v[4]; unsigned long long my[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) e[j] = (p0 + j < nn) ? o[p0 + j] : 0u;
+                        for (int j = 0; j < 4; j++) e[j] = (p0 + j < h) ? o[p0 + j] : 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        v[j] = (p0 + j < nn) ? value(e[j], f) : INFINITY;
-                    unsigned long long run = 0;
+                        for (int j = 0; j < 4; j++)
+                            v[j] = (p0 + j < h) ? value(e[j], f) : INFINITY;
+                        unsigned long long run = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        my[j] = (p0 + j < nn) ? ((unsigned long long)f16_w(e[j]) << (f16_y(e[j]) ? 32 : 0)) : 0ull;
-                        run += my[j];
+                        for (int j = 0; j < 4; j++) {
+                            my[j] = (p0 + j < h) ? ((unsigned long long)f16_w(e[j]) << (f16_y(e[j]) ? 32 : 0)) : 0ull;
+                            run += my[j];
+                        }
+                        unsigned long long incl = f16_warp_incl_scan_u64(run);
+                        unsigned long long ex = carry + incl - run;
+                        float vp = __shfl_up_sync(F16_FULL, v[3], 1);
+                        if (lane == 0) vp = prev_last;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int p = p0 + j;
+                            if (p < h && p > 0 && v[j] > __fadd_rn(vp, 1e-7f)) {
+                                int l0 = (int)(uint32_t)ex, l1 = (int)(ex >> 32);
+                                double proxy = gini_proxy(l0, l1, t0, t1);
+                                if (proxy > best.proxy) {
+                                    best.proxy = proxy; best.key = ((unsigned long long)k << 32) | (unsigned)p;
+                                    best.v_prev = vp; best.v = v[j]; best.l0 = l0; best.l1 = l1;
+                                }
+                            }
+                            ex += my[j]; vp = v[j];
+                        }
+                        carry += __shfl_sync(F16_FULL, incl, 31);
+                        prev_last = __shfl_sync(F16_FULL, v[3], 31);
                     }
-                    unsigned long long incl = f16_warp_incl_scan_u64(run);
-                    unsigned long long ex = carry + incl - run;
-                    float vp = __shfl_up_sync(F16_FULL, v[3], 1);
-                    if (lane == 0) vp = prev_last;
+                } else {
+                    // reversed element i stands for entry q = nn - 1 - i; its inclusive prefix is the
+                    // RIGHT sum of candidate position q (rows q .. nn-1); the candidate test compares
+                    // entry q with entry q - 1 = reversed element i + 1 (the lane's next element, the
+                    // next lane's first one, or - for lane 31 - one extra load)
+                    const int m = nn - h;                  // candidate positions h .. nn-1
+                    for (int base = 0; base < m; base += 128) {
+                        const int i0 = base + lane * 4;
+                        uint32_t e[4]; float v[4]; unsigned long long my[4];
+                        // element m (entry h - 1) is loaded for its value only
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int p = p0 + j;
-                        if (p < nn && p > 0 && v[j] > __fadd_rn(vp, 1e-7f)) {
-                            int l0 = (int)(uint32_t)ex, l1 = (int)(ex >> 32);
-                            double proxy = gini_proxy(l0, l1, t0, t1);
-                            if (proxy > best.proxy) {
-                                best.proxy = proxy; best.key = ((unsigned long long)k << 32) | (unsigned)p;
-                                best.v_prev = vp; best.v = v[j]; best.l0 = l0; best.l1 = l1;
+                        for (int j = 0; j < 4; j++) e[j] = (i0 + j <= m) ? o[nn - 1 - (i0 + j)] : 0u;
+                        const uint32_t e_after = (lane == 31 && i0 + 4 <= m) ? o[nn - 1 - (i0 + 4)] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            v[j] = (i0 + j <= m) ? value(e[j], f) : -INFINITY;
+                        float v_after = (lane == 31 && i0 + 4 <= m) ? value(e_after, f) : -INFINITY;
+                        unsigned long long run = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            my[j] = (i0 + j < m) ? ((unsigned long long)f16_w(e[j]) << (f16_y(e[j]) ? 32 : 0)) : 0ull;
+                            run += my[j];
+                        }
+                        unsigned long long incl = f16_warp_incl_scan_u64(run);
+                        unsigned long long r = carry + incl - run;
+                        const float vdown = __shfl_down_sync(F16_FULL, v[0], 1);
+                        if (lane != 31) v_after = vdown;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            r += my[j];
+                            const float vn = (j < 3) ? v[j < 3 ? j + 1 : 3] : v_after;     // entry q - 1
+                            if (i0 + j < m && v[j] > __fadd_rn(vn, 1e-7f)) {
+                                const int q = nn - 1 - (i0 + j);
+                                int l0 = t0 - (int)(uint32_t)r, l1 = t1 - (int)(r >> 32);
+                                double proxy = gini_proxy(l0, l1, t0, t1);
+                                const unsigned long long key = ((unsigned long long)k << 32) | (unsigned)q;
+                                if (proxy > best.proxy || (proxy == best.proxy && key < best.key)) {
+                                    best.proxy = proxy; best.key = key;
+                                    best.v_prev = vn; best.v = v[j]; best.l0 = l0; best.l1 = l1;
+                                }
                             }
                         }
-                        ex += my[j]; vp = v[j];
+                        carry += __shfl_sync(F16_FULL, incl, 31);
                     }
-                    carry += __shfl_sync(F16_FULL, incl, 31);
-                    prev_last = __shfl_sync(F16_FULL, v[3], 31);
                 }
             }
             // ---- block arg-max with (k, p) tie order
@@ -437,7 +496,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             PH_T(1, sm ? 9 : 8);
         }
     }
-    if (rtid == 0) { P.node_count[t] = c.node_count; atomicMax(P.err + 1, c.node_count); }
+    if (rtid == 0) { const int nc = min(c.node_count, P.node_cap); P.node_count[t] = nc; atomicMax(P.err + 1, nc); }
 }
 
 F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))

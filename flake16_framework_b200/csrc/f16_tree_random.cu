@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
             PH_T(0, 4);
         }
     }
-    if (rtid == 0) { P.node_count[t] = c.node_count; atomicMax(P.err + 1, c.node_count); }
+    if (rtid == 0) { const int nc = min(c.node_count, P.node_cap); P.node_count[t] = nc; atomicMax(P.err + 1, nc); }
 }
 
 F16_PHASE_READER(F16_CAT(f16_debug_phases, F16_VARIANT))

@@ -89,6 +89,19 @@ class _TreeEnsemble:
         self._forest.status()
         return self.classes_.take(pred.cpu().numpy().astype(np.intp))
 
+    def shap_values(self, X):
+        """``shap.TreeExplainer(self).shap_values(X)`` (get_shap, experiment.py:517): one float64
+        [n, d] array per class, path-dependent TreeSHAP on the device."""
+        if self._forest is None:
+            raise F16Error("This %s instance is not fitted yet." % type(self).__name__)
+        Xd, on_dev = _to_dev_f64(X)
+        if Xd.shape[1] != self.n_features_in_:
+            raise ValueError("X has %d features, but %s is expecting %d features as input."
+                             % (Xd.shape[1], type(self).__name__, self.n_features_in_))
+        Xrow = ops.rows_f32(Xd)
+        out = [self._forest.shap_values(Xrow, k) for k in (0, 1)]
+        return out if on_dev else [o.cpu().numpy() for o in out]
+
     @property
     def forest_(self):
         return self._forest

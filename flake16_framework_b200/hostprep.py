@@ -168,6 +168,47 @@ def stratified_kfold_test_folds(labels, n_splits=10, shuffle=True, random_state=
     return test_folds
 
 
+def stratified_group_kfold_test_folds(labels, groups, n_splits=5, shuffle=True, random_state=0):
+    """``StratifiedGroupKFold._iter_test_indices`` (sklearn/model_selection/_split.py, 1.9.0)
+    restated: the 5-fold project-grouped variant BASELINE.json's configs[1] names (the reference
+    itself uses the 10-fold splitter above).  Groups (projects) are dealt, in
+    order of decreasing spread of their class counts, to the fold that keeps the per-class
+    distribution over folds most even; ties go to the emptier fold.  Returns test_folds int[N]."""
+    y = np.asarray(labels)
+    _, y_inv, y_cnt = np.unique(y, return_inverse=True, return_counts=True)
+    if np.all(n_splits > y_cnt):
+        raise ValueError("n_splits=%d cannot be greater than the number of members in each class." % n_splits)
+    n_classes = len(y_cnt)
+    _, groups_inv, groups_cnt = np.unique(groups, return_inverse=True, return_counts=True)
+    n_groups = len(groups_cnt)
+    if n_splits > n_groups:
+        raise ValueError("Cannot have number of splits n_splits=%d greater than the number of groups: %d."
+                         % (n_splits, n_groups))
+    per_group = np.zeros((n_groups, n_classes))
+    np.add.at(per_group, (groups_inv, y_inv), 1)
+    if shuffle:
+        perm = np.arange(n_groups)
+        np.random.RandomState(random_state).shuffle(perm)          # legacy MT19937
+        per_group = per_group[perm]
+        inv_perm = np.empty_like(perm)
+        inv_perm[perm] = np.arange(perm.size)
+        groups_inv = inv_perm[groups_inv]
+    per_fold = np.zeros((n_splits, n_classes))
+    fold_of_group = np.empty(n_groups, dtype="i")
+    for g in np.argsort(-np.std(per_group, axis=1), kind="stable"):
+        best, min_eval, min_samples = None, np.inf, np.inf
+        for i in range(n_splits):
+            per_fold[i] += per_group[g]
+            fold_eval = np.mean(np.std(per_fold / y_cnt.reshape(1, -1), axis=0))
+            per_fold[i] -= per_group[g]
+            samples = np.sum(per_fold[i])
+            if fold_eval < min_eval or (np.isclose(fold_eval, min_eval) and samples < min_samples):
+                best, min_eval, min_samples = i, fold_eval, samples
+        per_fold[best] += per_group[g]
+        fold_of_group[g] = best
+    return fold_of_group[groups_inv]
+
+
 def kfold_split(test_folds, n_splits=10):
     for i in range(n_splits):
         mask = test_folds == i

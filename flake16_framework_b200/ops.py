@@ -126,6 +126,14 @@ class Forest:
         check(L.f16_forest_predict(self._h, _ptr(Xrow), Xrow.shape[0], _ptr(pred), _stream()))
         return pred
 
+    def shap_values(self, Xrow, klass=0):
+        """Path-dependent TreeSHAP of every row: float64 [n, d] (f16_forest_shap)."""
+        L = _lib.lib()
+        assert Xrow.dtype == torch.float32 and Xrow.shape[1] == padded_dim(self.d) and Xrow.is_contiguous()
+        phi = torch.empty((Xrow.shape[0], self.d), dtype=torch.float64, device=Xrow.device)
+        check(L.f16_forest_shap(self._h, _ptr(Xrow), Xrow.shape[0], int(klass), _ptr(phi), _stream()))
+        return phi
+
     def status(self):
         """Synchronises the current stream; raises if the device-side fit failed."""
         rc = _lib.lib().f16_forest_status(self._h, _stream())
@@ -354,6 +362,16 @@ def enn(X, y, clean_mask, n_neighbors=3):
     keep = torch.empty((X.shape[0],), dtype=torch.uint8, device=X.device)
     check(L.f16_enn_keep(_ptr(nn), n_neighbors + 1, _ptr(y), X.shape[0], clean_mask, _ptr(keep), _stream()))
     return _compact(X, y, keep, 1)
+
+
+# ----------------------------------------------------------------------------- figures
+def spearman(X64):
+    """scipy.stats.spearmanr(X).correlation for a device matrix: float64 [d, d]."""
+    L = _ready()
+    assert X64.dtype == torch.float64 and X64.is_contiguous() and X64.dim() == 2
+    rho = torch.empty((X64.shape[1], X64.shape[1]), dtype=torch.float64, device=X64.device)
+    check(L.f16_spearman(_ptr(X64), X64.shape[0], X64.shape[1], _ptr(rho), _stream()))
+    return rho
 
 
 # ----------------------------------------------------------------------------- scoring

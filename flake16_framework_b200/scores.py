@@ -46,9 +46,13 @@ def all_config_keys():
 class GridData:
     """Host-side, config-independent preparation: parse once, 12 datasets, 2 fold maps."""
 
-    def __init__(self, parsed, configs, n_splits=10):
+    def __init__(self, parsed, configs, n_splits=10, cv="stratified"):
+        """``cv``: "stratified" - the reference's StratifiedKFold(n_splits, shuffle=True,
+        random_state=0) (experiment.py:450); "group" - StratifiedGroupKFold with the projects as
+        groups (BASELINE.json configs[1]'s variant)."""
         self.parsed = parsed
         self.n_splits = n_splits
+        self.cv = cv
         all_features, raw_labels, projects = parsed
         self.projects = projects
         # project ids in order of first appearance == insertion order of the reference's
@@ -73,7 +77,8 @@ class GridData:
             self.datasets[(ft, fs, pre)], self.col_order[(ft, fs, pre)] = matrices[(fs, pre)]
             if ft not in self.labels:
                 self.labels[ft] = y
-                self.folds[ft] = hp.stratified_kfold_test_folds(y, n_splits, True, 0)
+                self.folds[ft] = (hp.stratified_kfold_test_folds(y, n_splits, True, 0) if cv == "stratified" else
+                                  hp.stratified_group_kfold_test_folds(y, projects, n_splits, True, 0))
 
 
 class _DeviceData:
@@ -169,8 +174,8 @@ def _minority_clean_mask(counts, strategy):
 class _NodeCaps:
     """Per-tree node capacity for f16_forest_fit_cap, learnt from the fits already settled: the
     worst case 2n - 1 costs 32 B x (2n - 1) per tree (1.1 GB per 100-tree forest at 178 k rows,
-    57 GB for 500 trees at 1.8 M), real trees of this path hold 0.03 n - 0.3 n nodes.  Key = (model,
-    d, resampled?); capacity = 1.5 x the largest nodes / n ratio seen + 1024.  The first fit of a
+    57 GB for 500 trees at 1.8 M), real trees of this path hold 0.03 n - 0.3 n nodes.  Key = the config
+    (dataset, balancing, model: its 10 folds are statistically alike); capacity = 1.5 x the largest nodes / n ratio seen + 1024.  The first fit of a
     key uses the worst case; if a later fit overflows its capacity (F16_ERR_OVERFLOW from
     f16_forest_status) run_grid repeats the whole pass with capacities disabled."""
 
@@ -268,7 +273,7 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
             with torch.cuda.stream(side):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
-                cap_key = (model, d, bal != "None")
+                cap_key = ds_key + (bal, model)
                 n_fit = Xrow.shape[0]
                 node_cap = caps.cap(cap_key, n_fit)
                 forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx, node_cap=node_cap)
@@ -288,21 +293,22 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
     return events, keep
 
 
-def prepare(parsed, configs=None, device=None, n_splits=10):
+def prepare(parsed, configs=None, device=None, n_splits=10, cv="stratified"):
     """Host preparation + upload: returns (GridData, device copies).  bench.py uses this to
     time the grid with its inputs already resident in HBM."""
     configs = list(configs) if configs is not None else all_config_keys()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     ops._ready(device.index if device.index is not None else torch.cuda.current_device())
-    gd = GridData(parsed, configs, n_splits)
+    gd = GridData(parsed, configs, n_splits, cv)
     dd = _DeviceData(gd, device)
     torch.cuda.synchronize(device)
     return gd, dd
 
 
 def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFAULT_WORKERS, device=None,
-             rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None, folds=None):
+             rank=0, world=1, progress=None, return_counts=False, prepared=None, stats=None, folds=None,
+             cv="stratified"):
     """Computes the scores dict for ``configs`` (default: the full 216 grid).
 
     Returns {config_keys: [t_train / n_splits, t_test / n_splits, scores, scores_total]} - the
@@ -310,13 +316,14 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFA
     configs = list(configs) if configs is not None else all_config_keys()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    gd, dd = prepared if prepared is not None else prepare(parsed, configs, device, n_splits)
+    gd, dd = prepared if prepared is not None else prepare(parsed, configs, device, n_splits, cv)
     if stats is not None:
         stats["h2d_bytes"] = dd.h2d_bytes()
     cfg_index = {c: i for i, c in enumerate(configs)}
     wanted, shards = plan_units(gd, configs, n_splits, world, folds)
     mine = shards[rank]
     n_lanes = int(os.environ.get("F16_LANES", str(DEFAULT_LANES)))
+    n_dt_lanes = int(os.environ.get("F16_DT_LANES", "2"))
 
     def one_pass(caps):
         """All of this rank's work items once; returns (counts, times, a fit overflowed its node capacity)."""
@@ -336,7 +343,7 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFA
             torch.cuda.set_device(device)
             stream = torch.cuda.Stream(device=device)
             # several forests of one item in flight: n_lanes side streams per forest model, 2 for the tree
-            model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(2 if m == "Decision Tree" else n_lanes)]
+            model_streams = {m: [torch.cuda.Stream(device=device) for _ in range(n_dt_lanes if m == "Decision Tree" else n_lanes)]
                              for m in MODELS}
             util = torch.cuda.Stream(device=device)     # status reads / frees of settled items
             pending = []
@@ -401,8 +408,11 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFA
 
     if world > 1:
         import torch.distributed as dist
+        on_host = dist.get_backend() != "nccl"        # e.g. gloo (tests: two ranks on one device)
+        tt = torch.from_numpy(times) if on_host else torch.from_numpy(times).to(device)
+        if on_host:
+            counts_all = counts_all.cpu()
         dist.all_reduce(counts_all, op=dist.ReduceOp.SUM)          # the one exchange step
-        tt = torch.from_numpy(times).to(device)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         times = tt.cpu().numpy()
     counts = counts_all.cpu().numpy()

@@ -102,6 +102,11 @@ int f16_forest_export(const f16_forest* forest, int32_t tree, int64_t n_nodes, i
                       int64_t* feature, double* threshold, double* impurity, int64_t* n_node_samples,
                       double* weighted_n_node_samples, double* value, void* stream);
 void f16_forest_free(f16_forest* forest, void* stream);
+/* shap.TreeExplainer(model).shap_values(features)[klass]  (get_shap, experiment.py:504-517): path-
+ * dependent TreeSHAP of the fitted forest for every row of X_dev (float32 [n][dp] rows as for
+ * predict), mean over the trees; phi_dev float64 [n][d].  Synchronises the stream once. */
+int f16_forest_shap(const f16_forest* forest, const float* X_dev, int64_t n, int32_t klass, double* phi_dev,
+                    void* stream);
 
 /* ---- balancing: balancing.fit_resample(features_train, labels_train)  (experiment.py:463-466)
  * Exact float64 brute-force k-NN (NearestNeighbors(k).fit(A).kneighbors(Q)); idx_dev int32
@@ -143,6 +148,12 @@ int f16_enn_keep(const int32_t* nn_dev, int32_t kk, const uint8_t* y_dev, int64_
 int f16_compact_rows(const double* X_dev, const uint8_t* y_dev, const uint8_t* keep_dev, int64_t n, int32_t d,
                      int32_t grouped, double* Xout_dev, uint8_t* yout_dev, int64_t* src_index_dev,
                      int64_t* n_out_dev, void* stream);
+
+/* ---- figures: the 16 x 16 Spearman table of write_figures (experiment.py:661-663,
+ * scipy.stats.spearmanr(features).correlation): average ranks (ties share the mean rank) per
+ * column of X_dev (float64 [n][d] row-major), then the Pearson correlation of the ranks.
+ * rho_dev float64 [d][d]. */
+int f16_spearman(const double* X_dev, int64_t n, int32_t d, double* rho_dev, void* stream);
 
 /* ---- scoring: the per-row loop of experiment.py:476-483.  counts_dev int64 [n_proj + 1][3]
  * (FP, FN, TP per project, last row = total), accumulated across calls (folds). */

@@ -286,3 +286,19 @@ def test_unit_plan_is_a_balanced_partition(world):
     # bench.py's parity check plans a single fold
     _, one = S.plan_units(gd, cfgs, 10, 1, folds=[0])
     assert len(one[0]) == 24 and all(u[1] == 0 for u in one[0])
+
+
+@pytest.mark.parametrize("flaky", ["NOD", "OD"])
+def test_stratified_group_kfold_matches_sklearn(flaky):
+    """BASELINE.json configs[1]'s splitter (5-fold StratifiedGroupKFold over the projects): the
+    restated fold map equals scikit-learn's, fold by fold."""
+    from sklearn.model_selection import StratifiedGroupKFold
+    from flake16_framework_b200 import hostprep as hp, synth
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(6000, 16))
+    X, y, proj = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[flaky], hp.FEATURE_SETS["Flake16"])
+    tf = hp.stratified_group_kfold_test_folds(y, proj, 5, True, 0)
+    ref = StratifiedGroupKFold(n_splits=5, shuffle=True, random_state=0)
+    for i, (tr, te) in enumerate(ref.split(X, y, groups=proj)):
+        assert np.array_equal(np.flatnonzero(tf == i), te)
+        assert np.array_equal(np.flatnonzero(tf != i), tr)
+        assert not set(proj[te]) & set(proj[tr])                 # no project on both sides
