@@ -455,7 +455,7 @@ def ours_arm(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_cfg * e2e_steps / float(dt.item()), "unit": UNIT, "steps": e2e_steps,
                "h2d_bytes_per_step": stats["h2d_bytes"], "d2h_bytes_per_step": stats["d2h_bytes"],
-               "includes": "json parse, host preprocessing, H2D, grid, D2H, pickle"}
+               "includes": "json parse, host preprocessing, H2D, grid, D2H, pickle", "breakdown_s_last_step": stats.get("breakdown_s")}
 
     if rank != 0:
         return 0

@@ -230,6 +230,7 @@ static __device__ unsigned long long f16_phase_nodes[2][F16_NPH];
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
 int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);
+int f16_launch_build_random_w(const F16FitParams& P, cudaStream_t st);
 int f16_launch_build_best_rf(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_build_best_dt(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

@@ -171,6 +171,9 @@ def _minority_clean_mask(counts, strategy):
     return 0b11 & ~(1 << minority)
 
 
+_PILOT_BYTES = 8 << 30      # worst-case node bytes of one forest above which its capacity is piloted
+
+
 class _NodeCaps:
     """Per-tree node capacity for f16_forest_fit_cap, learnt from the fits already settled: the
     worst case 2n - 1 costs 32 B x (2n - 1) per tree (1.1 GB per 100-tree forest at 178 k rows,
@@ -276,6 +279,15 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
                 cap_key = ds_key + (bal, model)
                 n_fit = Xrow.shape[0]
                 node_cap = caps.cap(cap_key, n_fit)
+                if node_cap == 0 and caps.enabled and model != "Decision Tree" and \
+                        64 * n_fit * n_estimators > _PILOT_BYTES:
+                    # the worst-case node arrays of this forest would not fit comfortably (57 GB for
+                    # 500 trees on 1.8 M rows): measure the node count on a few trees first
+                    pilot = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], min(8, n_estimators), 0, sorted_idx)
+                    pilot.status()
+                    caps.update(cap_key, n_fit, pilot.max_nodes())
+                    pilot.free()
+                    node_cap = caps.cap(cap_key, n_fit)
                 forest = ops.forest_fit(Xrow, yb, d, MODEL_KIND[model], n_estimators, 0, sorted_idx, node_cap=node_cap)
                 e1.record()
                 pred = forest.predict(Xte)
@@ -452,10 +464,17 @@ def write_scores(tests_file="tests.json", scores_file="scores.pkl", return_stats
             dist.init_process_group("nccl")
     t0 = time.time()
     parsed = hp.parse_tests(tests_file)
+    t1 = time.time()
+    if kw.get("prepared") is None:
+        kw["prepared"] = prepare(parsed, kw.get("configs"), kw.get("device"), kw.get("n_splits", 10), kw.get("cv", "stratified"))
+    t2 = time.time()
     scores = run_grid(parsed, rank=rank, world=world, **kw)
+    t3 = time.time()
     if rank == 0:
         with open(scores_file, "wb") as fd:
             pickle.dump(scores, fd)
+    stats["breakdown_s"] = {"json_parse": t1 - t0, "host_prep_h2d_knn_calibration": t2 - t1, "grid": t3 - t2,
+                            "pickle": time.time() - t3}
     if return_stats:
         return scores, time.time() - t0, stats
     return scores, time.time() - t0
