@@ -29,8 +29,6 @@ def _sources(tune):
         ("f16_tree_random.cu", "_et", ["-fmad=false", "-DF16_VARIANT=_et", "-DNT=%d" % t["ET_NT"],
                                         "-DF16_MINB=%d" % t["ET_MINB"], "-DF16_S16=%d" % t["ET_S16"],
                                         "-DF16_S8=%d" % t["ET_S8"]] + x),
-        ("f16_tree_random_w.cu", "", ["-fmad=false", "-DF16_WS16=%d" % t.get("ET_WS16", 64),
-                                      "-DF16_WS8=%d" % t.get("ET_WS8", 128)]),
         ("f16_tree_best.cu", "_rf", ["-fmad=false", "-DF16_VARIANT=_rf", "-DNT=%d" % t["RF_NT"],
                                       "-DF16_MINB=%d" % t["RF_MINB"], "-DF16_WITH_BOOTSTRAP"] + x),
         ("f16_tree_best.cu", "_dt", ["-fmad=false", "-DF16_VARIANT=_dt", "-DNT=%d" % t["DT_NT"],

@@ -223,8 +223,7 @@ static int forest_fit_impl(const float* X_dev, const uint8_t* y_dev, int64_t n, 
         F->has_ev = 1;
         FIT_TRY(cudaEventRecord(F->ev0, st));
     }
-    static const int et_warp = getenv("F16_ET_WARP") ? atoi(getenv("F16_ET_WARP")) : 0;
-    rc = (kind == F16_KIND_ET) ? (et_warp ? f16_launch_build_random_w(P, st) : f16_launch_build_random_et(P, st))
+    rc = (kind == F16_KIND_ET) ? f16_launch_build_random_et(P, st)
        : (kind == F16_KIND_RF) ? f16_launch_build_best_rf(P, dyn, st) : f16_launch_build_best_dt(P, dyn, st);
     if (rc) {
         f16_set_error("tree build kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));

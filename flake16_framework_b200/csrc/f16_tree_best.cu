@@ -88,6 +88,9 @@ int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t
 #endif
 
 // ------------------------------------------------------------------ best splitter
+#ifndef F16_WPU
+#define F16_WPU 8             // 32-entry tiles per round of the list partition (this many loads in flight + as many prefetched)
+#endif
 #ifndef F16_SPLIT_SCAN
 #define F16_SPLIT_SCAN 1     // two warps per evaluated feature when the CTA has them (see the candidate scan)
 #endif
@@ -107,14 +110,24 @@ __device__ __forceinline__ void warp_partition(const uint32_t* src, uint32_t* ds
                                                const uint32_t* side) {
     const int lane = threadIdx.x & 31;
     int run_l = 0;
-    constexpr int WPU = 8;
+    constexpr int WPU = F16_WPU;
     const unsigned lt = (1u << lane) - 1u;
     int base = 0;
-    // full rounds: 8 x 32 entries, every load issued before the first use
+    // full rounds of WPU x 32 entries; the entries of the NEXT round are loaded before this round's
+    // ranks are computed and stored, so a round never waits for a cold load of its own
+    uint32_t en[WPU];
+    if (32 * WPU <= n) {
+#pragma unroll
+        for (int j = 0; j < WPU; j++) en[j] = src[start + j * 32 + lane];
+    }
     for (; base + 32 * WPU <= n; base += 32 * WPU) {
         uint32_t e[WPU]; bool left[WPU];
 #pragma unroll
-        for (int j = 0; j < WPU; j++) e[j] = src[start + base + j * 32 + lane];
+        for (int j = 0; j < WPU; j++) e[j] = en[j];
+        if (base + 64 * WPU <= n) {
+#pragma unroll
+            for (int j = 0; j < WPU; j++) en[j] = src[start + base + 32 * WPU + j * 32 + lane];
+        }
 #pragma unroll
         for (int j = 0; j < WPU; j++) left[j] = side_get(side, f16_id(e[j]));
 #pragma unroll
@@ -358,16 +371,24 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                 unsigned long long carry = 0;
                 if (!rev) {
                     float prev_last = 0.f;
-                    // 4 consecutive entries per lane: all 8 loads of a round are in flight together,
-                    // one warp scan per 128 entries
+                    // 4 consecutive entries per lane: one warp scan per 128 entries; the entries of the
+                    // NEXT round are loaded while this round's value gathers are in flight (entry ->
+                    // value is a chain of two memory latencies; overlapped, a round costs one)
+                    uint32_t en[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) en[j] = (lane * 4 + j < h) ? o[lane * 4 + j] : 0u;
                     for (int base = 0; base < h; base += 128) {
                         const int p0 = base + lane * 4;
                         uint32_t e[4]; float v[4]; unsigned long long my[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) e[j] = (p0 + j < h) ? o[p0 + j] : 0u;
+                        for (int j = 0; j < 4; j++) e[j] = en[j];
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             v[j] = (p0 + j < h) ? value(e[j], f) : INFINITY;
+                        if (base + 128 < h) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) en[j] = (p0 + 128 + j < h) ? o[p0 + 128 + j] : 0u;
+                        }
                         unsigned long long run = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
@@ -400,17 +421,26 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     // entry q with entry q - 1 = reversed element i + 1 (the lane's next element, the
                     // next lane's first one, or - for lane 31 - one extra load)
                     const int m = nn - h;                  // candidate positions h .. nn-1
+                    // element m (entry h - 1) is loaded for its value only
+                    uint32_t en[4], en_after;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) en[j] = (lane * 4 + j <= m) ? o[nn - 1 - (lane * 4 + j)] : 0u;
+                    en_after = (lane == 31 && lane * 4 + 4 <= m) ? o[nn - 1 - (lane * 4 + 4)] : 0u;
                     for (int base = 0; base < m; base += 128) {
                         const int i0 = base + lane * 4;
                         uint32_t e[4]; float v[4]; unsigned long long my[4];
-                        // element m (entry h - 1) is loaded for its value only
 #pragma unroll
-                        for (int j = 0; j < 4; j++) e[j] = (i0 + j <= m) ? o[nn - 1 - (i0 + j)] : 0u;
-                        const uint32_t e_after = (lane == 31 && i0 + 4 <= m) ? o[nn - 1 - (i0 + 4)] : 0u;
+                        for (int j = 0; j < 4; j++) e[j] = en[j];
+                        const uint32_t e_after = en_after;
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             v[j] = (i0 + j <= m) ? value(e[j], f) : -INFINITY;
                         float v_after = (lane == 31 && i0 + 4 <= m) ? value(e_after, f) : -INFINITY;
+                        if (base + 128 < m) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) en[j] = (i0 + 128 + j <= m) ? o[nn - 1 - (i0 + 128 + j)] : 0u;
+                            en_after = (lane == 31 && i0 + 132 <= m) ? o[nn - 1 - (i0 + 132)] : 0u;
+                        }
                         unsigned long long run = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {

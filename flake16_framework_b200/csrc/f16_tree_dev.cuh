@@ -166,20 +166,24 @@ __device__ __forceinline__ void block_partition(const uint32_t* src, uint32_t* d
                                                 Pred pred, int (*s_wcnt)[PU][NW]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int run_l = 0, buf = 0;
+    // the entries of the NEXT round are loaded while this round's predicate gathers are in flight
+    uint32_t en[PU];
+#pragma unroll
+    for (int j = 0; j < PU; j++) { int p = j * NT + tid; en[j] = (p < n) ? src[start + p] : 0u; }
     for (int base = 0; base < n; base += NT * PU, buf ^= 1) {
         uint32_t e[PU]; bool valid[PU], left[PU]; unsigned bal[PU];
         const int nj = min(PU, (n - base + NT - 1) / NT);     // sub-tiles that exist (uniform)
 #pragma unroll
         for (int j = 0; j < PU; j++) {
-            if (j < nj) {
-                int p = base + j * NT + tid;
-                valid[j] = p < n;
-                e[j] = valid[j] ? src[start + p] : 0u;
-            }
+            if (j < nj) { valid[j] = base + j * NT + tid < n; e[j] = en[j]; }
         }
 #pragma unroll
         for (int j = 0; j < PU; j++) {
             if (j < nj) left[j] = valid[j] && pred(e[j], start + base + j * NT + tid);
+        }
+        if (base + NT * PU < n) {
+#pragma unroll
+            for (int j = 0; j < PU; j++) { int p = base + NT * PU + j * NT + tid; en[j] = (p < n) ? src[start + p] : 0u; }
         }
 #pragma unroll
         for (int j = 0; j < PU; j++) {
@@ -230,7 +234,6 @@ static __device__ unsigned long long f16_phase_nodes[2][F16_NPH];
 
 // launchers implemented in f16_tree_random.cu / f16_tree_best.cu
 int f16_launch_build_random_et(const F16FitParams& P, cudaStream_t st);
-int f16_launch_build_random_w(const F16FitParams& P, cudaStream_t st);
 int f16_launch_build_best_rf(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_build_best_dt(const F16FitParams& P, size_t dyn_smem, cudaStream_t st);
 int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t* w32, int words_per_tree, cudaStream_t st);

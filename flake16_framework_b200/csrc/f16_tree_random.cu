@@ -136,12 +136,20 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                 float mn[4], mx[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+                // the row ids of the NEXT step are loaded while this step's row gathers are in flight
+                // (ids -> rows is a chain of two memory latencies; overlapped, a step costs one)
+                uint32_t idn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { int i = sl + u * SPI; idn[u] = (sl < nn) ? f16_id(src[start + (i < nn ? i : sl)]) : 0u; }
                 for (int i0 = sl; i0 < nn; i0 += SPI * 4) {
-                    uint32_t id[4]; float4 v[4];
+                    float4 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { int i = i0 + u * SPI; id[u] = f16_id(src[start + (i < nn ? i : i0)]); }
+                    for (int u = 0; u < 4; u++) v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)idn[u] * DP) + q);
+                    const int i1 = i0 + SPI * 4;
+                    if (i1 < nn) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)id[u] * DP) + q);
+                        for (int u = 0; u < 4; u++) { int i = i1 + u * SPI; idn[u] = f16_id(src[start + (i < nn ? i : i1)]); }
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {     // tail slots re-read row i0: harmless for min/max
                         mn[0] = fminf(mn[0], v[u].x); mx[0] = fmaxf(mx[0], v[u].x);
@@ -221,13 +229,21 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                     const int qk = fk >> 2, ck = fk & 3;
                     unsigned long long acc = 0;
                     constexpr int RPS = NT / 4;                 // rows per sweep step
+                    uint32_t en[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { int i = (tid >> 2) + u * RPS; en[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
                     for (int i0 = tid >> 2; i0 < nn; i0 += RPS * 4) {
                         uint32_t e[4]; float4 v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) { int i = i0 + u * RPS; e[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
+                        for (int u = 0; u < 4; u++) e[u] = en[u];
 #pragma unroll
                         for (int u = 0; u < 4; u++)
                             v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)f16_id(e[u] == 0xffffffffu ? 0u : e[u]) * DP) + qk);
+                        const int i1 = i0 + RPS * 4;
+                        if (i1 < nn) {             // next step's entries, while the gathers are in flight
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { int i = i1 + u * RPS; en[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const float x = ck == 0 ? v[u].x : ck == 1 ? v[u].y : ck == 2 ? v[u].z : v[u].w;

@@ -12,8 +12,8 @@
 #pragma once
 #include "f16_tree_dev.cuh"
 
-template <int DP, int S>
-__device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const TreeStack& stk, const F16FitParams& P, F16Node* nodes,
+template <int DP, int S, class STK>
+__device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const STK& stk, const F16FitParams& P, F16Node* nodes,
                                 const float* s_col, uint16_t (*s_idx)[S], const uint8_t* s_y) {
     constexpr int SP = S + 1;
     constexpr int G = 32 / DP;               // row groups of the all-feature min/max sweep

@@ -182,8 +182,11 @@ class _NodeCaps:
     key uses the worst case; if a later fit overflows its capacity (F16_ERR_OVERFLOW from
     f16_forest_status) run_grid repeats the whole pass with capacities disabled."""
 
+    _seen = {}          # process-wide: ratios learnt by earlier runs seed the next run's capacities
+                        # (like the memory pool, warm state of the library; a first run starts empty)
+
     def __init__(self, enabled=True):
-        self.ratio, self.lock, self.enabled = {}, threading.Lock(), enabled
+        self.ratio, self.lock, self.enabled = dict(_NodeCaps._seen) if enabled else {}, threading.Lock(), enabled
 
     def cap(self, key, n):
         with self.lock:
@@ -193,6 +196,8 @@ class _NodeCaps:
     def update(self, key, n, max_nodes):
         with self.lock:
             self.ratio[key] = max(self.ratio.get(key, 0.0), max_nodes / float(n))
+            if self.enabled:
+                _NodeCaps._seen[key] = self.ratio[key]
 
 
 def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers, model_streams, caps):
@@ -276,8 +281,8 @@ def _run_unit(gd, dd, unit, wanted, cfg_index, counts_all, n_estimators, timers,
             with torch.cuda.stream(side):
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
-                cap_key = ds_key + (bal, model)
                 n_fit = Xrow.shape[0]
+                cap_key = ds_key + (bal, model, int(n_fit).bit_length())        # config + size class
                 node_cap = caps.cap(cap_key, n_fit)
                 if node_cap == 0 and caps.enabled and model != "Decision Tree" and \
                         64 * n_fit * n_estimators > _PILOT_BYTES:
