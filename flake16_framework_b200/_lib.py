@@ -121,6 +121,7 @@ SIGNATURES = {
     "f16_knn": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p], c_int),
     "f16_knn_tc_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),
     "f16_knn_umma_probe": ([c_void_p, c_int64, c_void_p, c_int64, c_int32, ctypes.POINTER(ctypes.c_float), c_void_p], c_int),
+    "f16_fill_u8": ([c_void_p, c_int32, c_int64, c_void_p], c_int),
     "f16_smote_generate": ([c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                             c_void_p, c_void_p], c_int),
     "f16_tomek_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),

@@ -145,6 +145,14 @@ extern "C" int f16_gather_i32(const int32_t* v_dev, const int64_t* idx_dev, int6
     return F16_OK;
 }
 
+// labels of the synthetic rows SMOTE appends (imblearn: y_new = full(n_new, minority class))
+extern "C" int f16_fill_u8(uint8_t* dst_dev, int32_t value, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && !dst_dev)) { f16_set_error("f16_fill_u8: bad arguments"); return F16_ERR_INVALID; }
+    if (n == 0) return F16_OK;
+    CUDA_TRY(cudaMemsetAsync(dst_dev, value, (size_t)n, (cudaStream_t)stream));
+    return F16_OK;
+}
+
 // ------------------------------------------------------------------ SMOTE interpolation
 // X_new[j] = C[row] + step[j] * (C[nn[row][1 + col]] - C[row]),  row = idx[j] / k, col = idx[j] % k
 // (imblearn/over_sampling/_smote/base.py _make_samples/_generate_samples); nn has k+1

@@ -9,6 +9,13 @@ matrices handed to the CUDA kernels are bit-identical to the reference's:
 * ``StandardScaler`` / ``ScalePCA``     <- ``CONFIG_GRID[2]`` experiment.py:82-86, used at :452-453
 * ``stratified_kfold_test_folds``      <- ``StratifiedKFold(10, shuffle=True, random_state=0)``
                                           experiment.py:450,458
+* ``stratified_group_kfold_test_folds`` <- the 5-fold project-grouped variant of BASELINE.json configs[1]
+
+Provenance: ``StandardScaler``, ``ScalePCA`` and the two fold-map functions are numpy
+TRANSLITERATIONS of scikit-learn 1.9.0 internals (``preprocessing/_data.py``, ``decomposition/_pca.py``
+covariance_eigh path, ``model_selection/_split.py``) - third-party code of the reference's dependency,
+not of the reference itself - kept statement for statement (some of scikit-learn's local names
+survive) because bit-identical folds and feature matrices are what the count parity rests on.
 """
 
 import json

@@ -329,7 +329,7 @@ def smote(X, y, n_min, n_maj, minority=1, seed=0, k_neighbors=5, idx_min=None):
                                ctypes.c_void_p(Xout.data_ptr() + n * d * 8), _stream()))
     yout = torch.empty((n + n_new,), dtype=torch.uint8, device=X.device)
     yout[:n].copy_(y)
-    yout[n:].fill_(minority)
+    check(L.f16_fill_u8(ctypes.c_void_p(yout.data_ptr() + n), int(minority), n_new, _stream()))
     return Xout, yout
 
 

@@ -131,6 +131,8 @@ int f16_knn_tc_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_
  * forces the mma.sync implementation, strategy 4 forces the tcgen05 one whatever the size). */
 int f16_knn_umma_probe(const double* A_dev, int64_t n, const double* Q_dev, int64_t nq, int32_t d, float* err_host,
                        void* stream);
+/* y_new = full(n_new, minority) of SMOTE's output labels (a device memset). */
+int f16_fill_u8(uint8_t* dst_dev, int32_t value, int64_t n, void* stream);
 /* SMOTE._make_samples: X_new[j] = C[row] + steps[j] * (C[nn[row][1 + col]] - C[row]) with
  * row = sample_idx[j] / k, col = sample_idx[j] % k; nn_dev int32 [n_min][k + 1] from f16_knn. */
 int f16_smote_generate(const double* C_dev, int64_t n_min, int32_t d, const int32_t* nn_dev, int32_t k,

@@ -88,6 +88,72 @@ __global__ void __launch_bounds__(256) k_tile(const float* __restrict__ X, const
     else if (mx == 12345.f) out[0] = mx;
 }
 
+// mode 3: what a tree CTA could do in its idle 32 KB: every warp owns two 32-row tiles (double buffer),
+// loads the NEXT tile's ids and issues its 16-byte cp.async gathers before it reduces the current tile.
+__global__ void __launch_bounds__(256, 4) k_pipe(const float* __restrict__ X, const uint32_t* __restrict__ ids, int n, float* out) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = reinterpret_cast<float*>(sm) + (size_t)warp * 2 * 32 * DP;      // [2][32][16]
+    const uint32_t* src = ids + (size_t)blockIdx.x * n;
+    const int ntiles = (n + 31) / 32;
+    float mn = 1e30f, mx = -1e30f;
+    auto issue = [&](int t, int buf, uint32_t myid) {
+        // lane l holds the id of row 32 t + l; lane handles (row = j * 8 + l / 4, quarter = l % 4), j = 0..3
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = j * 8 + (lane >> 2);
+            const uint32_t id = __shfl_sync(0xffffffffu, myid, r);
+            if (t * 32 + r < n) {
+                const float* g = X + (size_t)id * DP + (lane & 3) * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile + (buf * 32 + r) * DP + (lane & 3) * 4)), "l"(g));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::);
+    };
+    int t = warp;                       // tiles warp, warp + 8, ...
+    uint32_t idc = (t < ntiles && t * 32 + lane < n) ? src[t * 32 + lane] : 0u;
+    int buf = 0;
+    if (t < ntiles) issue(t, 0, idc);
+    uint32_t idn = (t + 8 < ntiles && (t + 8) * 32 + lane < n) ? src[(t + 8) * 32 + lane] : 0u;
+    for (; t < ntiles; t += 8, buf ^= 1) {
+        if (t + 8 < ntiles) issue(t + 8, buf ^ 1, idn);
+        const int t2 = t + 16;
+        idn = (t2 < ntiles && t2 * 32 + lane < n) ? src[t2 * 32 + lane] : 0u;
+        if (t + 8 < ntiles) asm volatile("cp.async.wait_group 1;" ::); else asm volatile("cp.async.wait_group 0;" ::);
+        __syncwarp();
+        const int cnt = min(32, n - t * 32);
+        for (int r = lane >> 4; r < cnt; r += 2) { float v = tile[(buf * 32 + r) * DP + (lane & 15)]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+        __syncwarp();
+    }
+    if (mn > mx) out[blockIdx.x * 256 + threadIdx.x] = mn;
+    else if (mx == 12345.f) out[0] = mx;
+}
+
+template <int U>
+__global__ void __launch_bounds__(256, 4) k_ldg_occ4(const float* __restrict__ X, const uint32_t* __restrict__ ids, int n, float* out) {
+    extern __shared__ __align__(128) unsigned char sm[];      // 40 KB of padding: 4 CTAs per SM like the tree kernel
+    const uint32_t* src = ids + (size_t)blockIdx.x * n;
+    const int q = threadIdx.x & 3, sl = threadIdx.x >> 2;
+    float mn = 1e30f, mx = -1e30f;
+    uint32_t idn[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { int i = sl + u * 64; idn[u] = src[i < n ? i : sl]; }
+    for (int i0 = sl; i0 < n; i0 += 64 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)idn[u] * DP) + q);
+        const int i1 = i0 + 64 * U;
+        if (i1 < n) {
+#pragma unroll
+            for (int u = 0; u < U; u++) { int i = i1 + u * 64; idn[u] = src[i < n ? i : i1]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { mn = fminf(mn, fminf(fminf(v[u].x, v[u].y), fminf(v[u].z, v[u].w))); mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w))); }
+    }
+    if (mn > mx) { out[blockIdx.x * 256 + threadIdx.x] = mn; sm[threadIdx.x] = 1; }
+    else if (mx == 12345.f) out[0] = mx;
+}
+
 int main(int argc, char** argv) {
     const int n = 90000, trees = argc > 1 ? atoi(argv[1]) : 1184;
     std::vector<float> hX((size_t)n * DP);
@@ -128,6 +194,14 @@ int main(int argc, char** argv) {
         run("bulk 64 B/row, tile 128 rows/warp, 8 warps", [&] { k_tile<128, 2><<<trees, 256, smem(8, 128)>>>(X, ids, n, out); });
         run("bulk 64 B/row, tile 256 rows/warp, 1 warp", [&] { k_tile<256, 2><<<trees, 32, smem(1, 256)>>>(X, ids, n, out); });
         run("bulk 64 B/row, tile 128 rows/warp, 2 warps", [&] { k_tile<128, 2><<<trees, 64, smem(2, 128)>>>(X, ids, n, out); });
+    }
+    {
+        cudaFuncSetAttribute(k_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
+        cudaFuncSetAttribute(k_ldg_occ4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
+        cudaFuncSetAttribute(k_ldg_occ4<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
+        run("LDG x4 in flight + id prefetch, 4 CTAs/SM (tree kernel today)", [&] { k_ldg_occ4<4><<<trees, 256, 40 * 1024>>>(X, ids, n, out); });
+        run("LDG x8 in flight + id prefetch, 4 CTAs/SM", [&] { k_ldg_occ4<8><<<trees, 256, 40 * 1024>>>(X, ids, n, out); });
+        run("cp.async 32-row tiles, double buffered per warp, 4 CTAs/SM", [&] { k_pipe<<<trees, 256, 40 * 1024>>>(X, ids, n, out); });
     }
     return 0;
 }
