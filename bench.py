@@ -394,12 +394,21 @@ def ours_arm(args):
 
     for _ in range(args.warmup):
         one_step()
-    cpu_sample = None
-    if cpu_proc is not None:            # the CPU sample must be over before anything is timed
+    # untimed single-kernel probes and the parity pass come BEFORE the timed region: they fill the
+    # wait for the CPU sample (which must be over before anything is timed) instead of following it
+    probes = {}
+    if world == 1 and not args.no_probes:
+        probes["roofline"] = tree_roofline_probe(parsed, L, "RF")
+        probes["roofline_et"] = tree_roofline_probe(parsed, L, "ET")
+        probes["roofline_knn"] = knn_roofline_probe(parsed)
+    cpu_sample, cpu_res, parity = None, None, None
+    if cpu_proc is not None:
         _, err = cpu_proc.communicate()
         if cpu_proc.returncode != 0:
             raise RuntimeError("CPU sample failed:\n" + err.decode()[-2000:])
         cpu_sample = json.load(open(cpu_out))
+        cpu_res = [(tuple(k), t, c, tot) for k, t, c, tot in cpu_sample["results"]]
+        parity = parity_check(cpu_res, S, parsed, dev, args.streams, args.n_estimators)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -471,12 +480,9 @@ def ours_arm(args):
             "device_memory_in_use_bytes": int(peak_mem)}
     rc = 0
     if world == 1:
-        if not args.no_probes:
-            line["roofline"] = tree_roofline_probe(parsed, L, "RF")
-            line["roofline_et"] = tree_roofline_probe(parsed, L, "ET")
-            line["roofline_knn"] = knn_roofline_probe(parsed)
+        line.update(probes)
         if cpu_sample is not None:
-            res = [(tuple(k), t, c, tot) for k, t, c, tot in cpu_sample["results"]]
+            res = cpu_res
             wall, workers = cpu_sample["wall"], cpu_sample["workers"]
             est = cpu_grid_estimate(res)
             line["cpu_baseline"] = {"value": est["value"], "unit": UNIT, "cores": workers, "kind": "port",
@@ -484,8 +490,8 @@ def ours_arm(args):
                                               " (%.0f s; run in a separate process during this arm's untimed preparation "
                                               "and warm-up, finished before the timed region)" % wall,
                                     "host_cores": os.cpu_count(), "estimate": est}
-            line["parity_check"] = parity_check(res, S, parsed, dev, args.streams, args.n_estimators)
-            if not line["parity_check"]["identical"]:
+            line["parity_check"] = parity
+            if not parity["identical"]:
                 rc = 1
     print(json.dumps(line), flush=True)
     return rc
