@@ -40,6 +40,7 @@ __device__ void subtree_warp_v2(Ctl& c, DrawState& ds, const STK& stk, const F16
 
     while (sp > 0) {
         F16StackRec r = stk.get(sp - 1);
+        __syncwarp();                           // every lane holds the record before lane 0 reuses its slot
         if (!r.pad) break;                      // back to a node that lives in global memory
         sp--;
         const int start = r.start, nn = r.end - r.start;

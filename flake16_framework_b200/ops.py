@@ -90,6 +90,14 @@ def argsort_columns(Xrow, d):
     return out
 
 
+def zero_bytes(t):
+    """Device memset of a contiguous tensor's storage (f16_fill_u8)."""
+    L = _ready()
+    assert t.is_contiguous()
+    check(L.f16_fill_u8(_ptr(t), 0, t.numel() * t.element_size(), _stream()))
+    return t
+
+
 # ----------------------------------------------------------------------------- forests
 def tree_seeds(seed, kind, n_trees):
     L = _lib.lib()

@@ -344,8 +344,9 @@ def run_grid(parsed, configs=None, n_splits=10, n_estimators=100, n_streams=DEFA
 
     def one_pass(caps):
         """All of this rank's work items once; returns (counts, times, a fit overflowed its node capacity)."""
-        counts_all = torch.zeros((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
-        # the zero fill runs on the caller's stream; the workers' non-blocking streams must not
+        counts_all = torch.empty((len(configs), gd.n_proj + 1, 3), dtype=torch.int64, device=device)
+        ops.zero_bytes(counts_all)
+        # the memset runs on the caller's stream; the workers' non-blocking streams must not
         # start accumulating before it has completed
         torch.cuda.current_stream(device).synchronize()
         times = np.zeros((len(configs), 2), dtype=np.float64)

@@ -22,3 +22,18 @@ for cls in (E.TomekLinks, E.SMOTE, E.EditedNearestNeighbours, E.SMOTEENN, E.SMOT
     Xr, yr = cls(**kw).fit_resample(X, y)
     print(cls.__name__, Xr.shape, int(yr.sum()), flush=True)
 print("SMOKE_OK")
+# round 2: TreeSHAP, Spearman, the grid engine with learnt node capacities
+m = E.ExtraTreesClassifier(random_state=0, n_estimators=3).fit(X, y)
+phi = m.shap_values(X[:200])
+print("shap", phi[0].shape, float(np.abs(phi[0]).max()), float(np.abs(phi[0] + phi[1]).max()), flush=True)
+rho = ops.spearman(torch.from_numpy(np.ascontiguousarray(X)).cuda()).cpu().numpy()
+print("spearman", rho.shape, float(np.abs(np.diag(rho) - 1).max()), flush=True)
+if len(sys.argv) > 2:
+    from flake16_framework_b200 import scores as S, hostprep as hp, synth
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(n, 16))
+    cfgs = [c for c in S.all_config_keys() if c[:3] == ("NOD", "Flake16", "Scaling")]
+    prep = S.prepare(parsed, cfgs)
+    for rep in range(2):
+        out = S.run_grid(parsed, cfgs, prepared=prep, n_streams=2)
+    print("grid", len(out), sum(v[3][2] for v in out.values()), flush=True)
+print("SMOKE2_OK")
