@@ -302,3 +302,41 @@ def test_stratified_group_kfold_matches_sklearn(flaky):
         assert np.array_equal(np.flatnonzero(tf == i), te)
         assert np.array_equal(np.flatnonzero(tf != i), tr)
         assert not set(proj[te]) & set(proj[tr])                 # no project on both sides
+
+
+def test_oracle_pinned_against_reference_golden_n20000(tmp_path):
+    """The oracle restatement against the second, larger reference-generated golden (20 000 tests)
+    on two configurations that finish in seconds."""
+    path = os.path.join(GOLD, "scores_n20000_seed16.pkl")
+    if not os.path.exists(path):
+        pytest.skip("scores_n20000_seed16.pkl not generated")
+    import ref_scores as R
+    from flake16_framework_b200 import synth
+    gold = pickle.load(open(path, "rb"))
+    p = str(tmp_path / "tests.json")
+    synth.make_tests_json(p, 20000, 16)
+    for cfg in (("NOD", "Flake16", "None", "None", "Decision Tree"), ("OD", "FlakeFlagger", "Scaling", "None", "Extra Trees")):
+        _, (keys, _, _, per_proj, total) = R.get_scores(cfg, p, R.make_config_grid())
+        g_proj, g_total = gold[cfg]
+        assert [int(v) for v in total[:3]] == g_total, cfg
+        assert {str(k): [int(x) for x in v[:3]] for k, v in per_proj.items()} == g_proj, cfg
+
+
+def test_bench_cpu_arm_is_a_fixed_sample_and_extrapolates_with_grid_multiplicities():
+    """bench.py's CPU arm: the sample does not depend on --steps, covers all 18
+    (balancing x model) kinds on one Flake16 and one FlakeFlagger dataset, and the grid estimate is
+    6 x the sum of the sampled configs' (setup + 10 x fold) seconds over min(cores, 216) workers."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tasks = bench.cpu_sample_tasks()
+    assert len(tasks) == 36 and len(set(tasks)) == 36
+    assert {t[3] for t in tasks} == set(bench.BALANCINGS) and {t[4] for t in tasks} == set(bench.MODELS)
+    assert {t[:3] for t in tasks} == set(bench.CPU_SAMPLE_DATASETS)
+    assert any("Tomek" in t[3] for t in tasks) and any("ENN" in t[3] for t in tasks)
+    res = [(t, {"setup_s": 1.0, "folds_s": 2.0 + i}, {}, [0, 0, 0]) for i, t in enumerate(tasks)]
+    est = bench.cpu_grid_estimate(res)
+    core_s = 6.0 * sum(1.0 + 10.0 * (2.0 + i) for i in range(36))
+    pool = min(os.cpu_count() or 1, 216)
+    assert abs(est["cpu_core_s_estimate"] - core_s) < 1e-9
+    assert abs(est["value"] - 216.0 / (core_s / pool)) < 1e-12
+    assert abs(est["slowest_config_s_estimate"] - (1.0 + 10.0 * 37.0)) < 1e-9

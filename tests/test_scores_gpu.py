@@ -50,6 +50,23 @@ def test_full_grid_matches_reference_golden(cuda):
                 assert (a is None and b is None) or abs(a - b) <= 1e-6
 
 
+def test_full_grid_matches_reference_golden_n20000(cuda):
+    """All 216 configs at 20 000 tests against the reference's own write_scores() output
+    (tests/golden/make_golden_n20000.py).  The SMOTE'd training sets (~35 000 rows) of the Scaling /
+    PCA datasets take the tensor-core k-NN filter inside the product flow (n x nq >= 2.5e8), the raw
+    ones the early-exit float64 search; the forests hold 100 trees on 18 000 - 35 000 rows."""
+    path = os.path.join(GOLD, "scores_n20000_seed16.pkl")
+    if not os.path.exists(path):
+        pytest.skip("scores_n20000_seed16.pkl not generated")
+    from flake16_framework_b200 import scores as S, hostprep as hp, synth
+    parsed = hp.tests_to_arrays(synth.make_tests_dict(20000, 16))
+    scores = S.run_grid(parsed, n_streams=4)
+    gold = pickle.load(open(path, "rb"))
+    assert len(scores) == 216 and len(gold) == 216
+    bad = _cmp(scores, gold)
+    assert not bad, "%d/216 configs differ, first: %r" % (len(bad), bad[:5])
+
+
 def test_cli_drop_in(cuda, tmp_path):
     """`python experiment.py scores` reads ./tests.json and writes ./scores.pkl with the
     reference's schema (experiment.py:488-490,498-501)."""
