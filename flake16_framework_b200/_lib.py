@@ -35,6 +35,7 @@ def _sources(tune):
                                       "-DF16_MINB=%d" % t["DT_MINB"]] + x),
         ("f16_shap.cu", "", []),
         ("f16_stats.cu", "", []),
+        ("f16_parse.cu", "", []),
         ("f16_misc.cu", "", ["-fmad=false"]),
         ("f16_sort.cu", "", []),
         ("f16_knn.cu", "", ["-DKQ=%d" % t.get("KNN_KQ", 2), "-DKNN_UNROLL=%d" % t.get("KNN_UNROLL", 1)]),
@@ -128,6 +129,13 @@ SIGNATURES = {
     "f16_enn_keep": ([c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
     "f16_compact_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p], c_int),
+    "f16_tests_parse": ([ctypes.c_char_p, ctypes.POINTER(c_void_p)], c_int),
+    "f16_tests_rows": ([c_void_p], c_int64),
+    "f16_tests_cols": ([c_void_p], c_int32),
+    "f16_tests_projects": ([c_void_p], c_int32),
+    "f16_tests_names_bytes": ([c_void_p], c_int64),
+    "f16_tests_copy": ([c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "f16_tests_free": ([c_void_p], None),
     "f16_confusion": ([c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p], c_int),
 }
 

@@ -45,9 +45,46 @@ def parse_tests(path):
     (experiment.py:449 -> :411-412); the parse result does not depend on the config, so
     the grid engine calls this once and derives the 4 (label, feature-set) views below.
     """
+    fast = _parse_tests_native(path)
+    if fast is not None:
+        return fast
     with open(path, "r") as fd:
         tests = json.load(fd)
     return tests_to_arrays(tests)
+
+
+def _parse_tests_native(path):
+    """The same three arrays through the library's one-pass scanner (f16_tests_parse: strtod for
+    every number, so the float64 values are the ones ``json.load`` yields); None if the library is
+    not built or the file is not in the plain ``write_tests`` format - the caller then uses json."""
+    import ctypes
+    try:
+        from . import _lib
+        L = _lib.lib()
+    except Exception:
+        return None
+    h = ctypes.c_void_p()
+    if L.f16_tests_parse(str(path).encode(), ctypes.byref(h)) != 0:
+        return None
+    try:
+        n, cols, n_proj = L.f16_tests_rows(h), L.f16_tests_cols(h), L.f16_tests_projects(h)
+        if n == 0 or cols < 3:
+            return None
+        values = np.empty((n, cols), dtype=np.float64)
+        proj = np.empty(n, dtype=np.int32)
+        names = ctypes.create_string_buffer(max(1, L.f16_tests_names_bytes(h)))
+        if L.f16_tests_copy(h, values.ctypes.data, proj.ctypes.data, names) != 0:
+            return None
+    finally:
+        L.f16_tests_free(h)
+    labels = values[:, 1]
+    if not np.array_equal(labels, np.floor(labels)):
+        return None
+    name_list = names.raw[:-1].decode("utf-8").split("\0") if n_proj else []
+    if len(name_list) != n_proj:
+        return None
+    # same objects as tests_to_arrays: C-contiguous float64 features, int64 labels, <U project names
+    return (np.ascontiguousarray(values[:, 2:]), labels.astype(np.int64), np.array(name_list)[proj])
 
 
 def tests_to_arrays(tests):

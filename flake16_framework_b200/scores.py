@@ -69,10 +69,22 @@ class GridData:
         self.labels = {}        # ft -> bool[N]
         self.folds = {}         # ft -> test_folds int[N]
         matrices = {}           # (fs, pre) -> (matrix, column order): independent of the flaky type
+        scaled = {}
+        by_fs, by_ft = {}, {}   # the feature view depends on the feature set only, the labels on the flaky type only
         for (ft, fs, pre) in sorted({c[:3] for c in configs}):
-            X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[ft], hp.FEATURE_SETS[fs])
+            if fs not in by_fs or ft not in by_ft:
+                Xv, yv, _ = hp.feat_lab_proj(parsed, hp.FLAKY_TYPES[ft], hp.FEATURE_SETS[fs])
+                by_fs.setdefault(fs, Xv)
+                by_ft.setdefault(ft, yv)
+            X, y = by_fs[fs], by_ft[ft]
             if (fs, pre) not in matrices:
-                M = np.ascontiguousarray(hp.preprocess(X, pre))
+                if pre == "None":
+                    M = X
+                else:        # the StandardScaler output of a feature set serves "Scaling" and, as PCA's input, "PCA"
+                    if fs not in scaled:
+                        scaled[fs] = hp.StandardScaler().fit_transform(X)
+                    M = scaled[fs] if pre == "Scaling" else hp.PCA().fit_transform(scaled[fs])
+                M = np.ascontiguousarray(M)
                 matrices[(fs, pre)] = (M, ops.variance_order(M))
             self.datasets[(ft, fs, pre)], self.col_order[(ft, fs, pre)] = matrices[(fs, pre)]
             if ft not in self.labels:

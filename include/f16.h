@@ -46,6 +46,21 @@ long long f16_launch_count(int reset);
 void f16_set_profiling(int on);
 double f16_forest_build_ms(const f16_forest* forest);
 
+/* ---- input: the parse step of load_feat_lab_proj (experiment.py:410-421), host only.
+ * One-pass scanner for the tests.json wire format write_tests emits ({project: {test id: [req_runs,
+ * label, f0..f15]}}); numbers are read with strtod, i.e. exactly as Python's json does.  Returns
+ * F16_ERR_INVALID for anything outside that format (the Python layer then uses the json module).
+ * f16_tests_copy: values_host float64 [rows][cols], proj_host int32 [rows] (index into the project
+ * names, file order), names_host the names NUL separated (f16_tests_names_bytes bytes). */
+typedef struct f16_tests f16_tests;
+int f16_tests_parse(const char* path, f16_tests** out);
+int64_t f16_tests_rows(const f16_tests* t);
+int32_t f16_tests_cols(const f16_tests* t);
+int32_t f16_tests_projects(const f16_tests* t);
+int64_t f16_tests_names_bytes(const f16_tests* t);
+int f16_tests_copy(const f16_tests* t, double* values_host, int32_t* proj_host, char* names_host);
+void f16_tests_free(f16_tests* t);
+
 /* ---- data staging ------------------------------------------------------------------
  * features[train] / features[test] (experiment.py:459-460) fused with the float32 cast that
  * sklearn applies in BaseForest.fit / predict.  X_dev: float64 [N][d] row-major; idx_dev: int64

@@ -1,5 +1,6 @@
 """CPU tests (no GPU): host logic, oracle vs golden fixtures, C-ABI surface."""
 import ctypes
+import json
 import os
 import pickle
 import re
@@ -340,3 +341,39 @@ def test_bench_cpu_arm_is_a_fixed_sample_and_extrapolates_with_grid_multipliciti
     assert abs(est["cpu_core_s_estimate"] - core_s) < 1e-9
     assert abs(est["value"] - 216.0 / (core_s / pool)) < 1e-12
     assert abs(est["slowest_config_s_estimate"] - (1.0 + 10.0 * 37.0)) < 1e-9
+
+
+def test_native_tests_json_parser_equals_json_module(tmp_path):
+    """hostprep.parse_tests reads tests.json with the library's one-pass scanner (f16_tests_parse);
+    the arrays must be the ones json.load + the reference's loop give, bit for bit - on the
+    synthetic table and on a hand-made file with the awkward cases (exponents, negative and huge
+    numbers, "-0", escapes and unicode in test ids, odd whitespace)."""
+    from flake16_framework_b200 import hostprep as hp, synth
+    p = str(tmp_path / "tests.json")
+    synth.make_tests_json(p, 3000, 16)
+    a = hp._parse_tests_native(p)
+    assert a is not None, "the library's scanner rejected the synthetic file"
+    b = hp.tests_to_arrays(json.load(open(p)))
+    assert np.array_equal(a[0].view(np.int64), b[0].view(np.int64)) and a[0].flags["C_CONTIGUOUS"]
+    assert np.array_equal(a[1], b[1]) and a[1].dtype == b[1].dtype
+    assert np.array_equal(a[2], b[2]) and a[2].dtype == b[2].dtype
+    row = [0, 2, 1e-7, -3.5e+10, 123456789012345678901234567890, -0, 0.1, 1E3, 2.2250738585072014e-308,
+           17, 5e-324, 1.7976931348623157e308, 9007199254740993, 3, 4, 5.000000000000001, 6, 7.25]
+    odd = {"proj\u00e9t": {'t::a["x\\y"]': row, "t\u00e9::b": [1, 0] + [float(i) / 3 for i in range(16)]},
+           "p2": {"n": [2, 1] + list(range(16))}}
+    text = json.dumps(odd, indent=4, ensure_ascii=False).replace("[\n", "[ \t\n").replace(",\n", " ,\r\n")
+    q = str(tmp_path / "odd.json")
+    open(q, "w", encoding="utf-8").write(text)
+    a = hp._parse_tests_native(q)
+    b = hp.tests_to_arrays(json.load(open(q, encoding="utf-8")))
+    assert a is not None
+    assert np.array_equal(a[0].view(np.int64), np.asarray(b[0], dtype=np.float64).view(np.int64))
+    assert np.array_equal(a[1], b[1]) and list(a[2]) == list(b[2])
+    # outside the format: the scanner declines and parse_tests falls back to the json module
+    r = str(tmp_path / "ragged.json")
+    json.dump({"p": {"a": [0, 1, 2.0, 3.0], "b": [0, 1, 2.0]}}, open(r, "w"))
+    assert hp._parse_tests_native(r) is None
+    e = str(tmp_path / "esc.json")
+    json.dump({"p\\q": {"a": [0, 1, 2.0]}}, open(e, "w"))
+    assert hp._parse_tests_native(e) is None
+    assert list(hp.parse_tests(e)[2]) == ["p\\q"]
