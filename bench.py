@@ -165,7 +165,7 @@ def cpu_sample_subprocess(args, tests_file, out_file):
     arm prepares and warms up - untimed work on both sides; it is joined BEFORE the timed region."""
     cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-out", out_file, "--cpu-sample-tests", tests_file,
            "--n-estimators", str(args.n_estimators)]
-    return subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=open(out_file + ".err", "w"))
 
 
 def cpu_sample_worker_main(args):
@@ -403,9 +403,8 @@ def ours_arm(args):
         probes["roofline_knn"] = knn_roofline_probe(parsed)
     cpu_sample, cpu_res, parity = None, None, None
     if cpu_proc is not None:
-        _, err = cpu_proc.communicate()
-        if cpu_proc.returncode != 0:
-            raise RuntimeError("CPU sample failed:\n" + err.decode()[-2000:])
+        if cpu_proc.wait() != 0:
+            raise RuntimeError("CPU sample failed:\n" + open(cpu_out + ".err").read()[-2000:])
         cpu_sample = json.load(open(cpu_out))
         cpu_res = [(tuple(k), t, c, tot) for k, t, c, tot in cpu_sample["results"]]
         parity = parity_check(cpu_res, S, parsed, dev, args.streams, args.n_estimators)

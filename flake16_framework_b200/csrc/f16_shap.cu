@@ -14,7 +14,7 @@
 // 8-point Gauss-Legendre rule.  Per (row, path) that is 8 m multiply-adds for the full products and
 // 8 m for the leave-one-out sums (a multiplication by the reciprocal of the factor, which takes one
 // of two path constants) - no recursion, no data-dependent control flow, no divisions in the inner
-// loop.  It equals the EXTEND / UNWIND result to 1e-15 relative (tests/test_shap_gpu.py).
+// loop.  It equals the EXTEND / UNWIND result to 1e-15 relative (tests/test_explain_gpu.py).
 //
 // Kernels: k_shap_leaves (leaf ids of every tree, in node order), k_shap_paths (one thread per leaf
 // walks down from the root - pre-order numbering makes "is the leaf in the left subtree" the test
@@ -248,13 +248,20 @@ extern "C" int f16_forest_shap(const f16_forest* F, const float* X_dev, int64_t 
     std::vector<long long> off(T + 1, 0);
     long long n_paths = 0, ppc = 0;
     int n_chunks = 1, max_leaves = 0;
+    int32_t fit_err = 0;
     size_t smem = shap_smem_bytes();
     CUDA_TRY(f16_malloc_async((void**)&leaf_ids, sizeof(int32_t) * (size_t)T * leaf_stride, st));
     CUDA_TRY(f16_malloc_async((void**)&n_leaves, sizeof(int32_t) * T, st));
     k_shap_leaves<<<T, 32, 0, st>>>(F->nodes, F->node_cap, F->node_count, leaf_ids, leaf_stride, n_leaves);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(nl.data(), n_leaves, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&fit_err, F->err, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (fit_err != 0) {        // a forest whose fit was aborted holds dangling links: refuse to walk it
+        f16_set_error("f16_forest_shap: the forest's fit failed on the device (code %d)", fit_err);
+        rc = fit_err;
+        goto done;
+    }
     for (int t = 0; t < T; t++) { off[t + 1] = off[t] + nl[t]; if (nl[t] > max_leaves) max_leaves = nl[t]; }
     n_paths = off[T];
     CUDA_TRY(f16_malloc_async((void**)&path_off, sizeof(long long) * (T + 1), st));
