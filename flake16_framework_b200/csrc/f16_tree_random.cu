@@ -221,18 +221,23 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                 //      holds candidate t's feature, so a warp's load touches 8 rows = 8 lines (four
                 //      scalar gathers per row cost four times the L1 wavefronts).  `x <= thr` for a
                 //      float32 x and a float64 thr is decided in float32 against thr rounded down.
+                //      With one or two candidates in the chunk (max_features = 2 for the 7-feature
+                //      sets, or constant features) one / two threads share a row instead of four, so no
+                //      thread repeats another's work: 1 << sh threads per row.
                 for (int k0 = 0; k0 < ncand; k0 += 4) {
-                    const int t4 = tid & 3;
-                    const int k = (k0 + t4 < ncand) ? k0 + t4 : k0;
+                    const int nck = min(4, ncand - k0);
+                    const int sh = (nck == 1) ? 0 : (nck == 2) ? 1 : 2;
+                    const int tr = tid & ((1 << sh) - 1);
+                    const int k = (k0 + tr < ncand) ? k0 + tr : k0;
                     const int fk = s_cand_f[k];
                     const float tk = __double2float_rd(s_cand_thr[k]);
                     const int qk = fk >> 2, ck = fk & 3;
                     unsigned long long acc = 0;
-                    constexpr int RPS = NT / 4;                 // rows per sweep step
+                    const int RPS = NT >> sh;                   // rows per sweep step
                     uint32_t en[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { int i = (tid >> 2) + u * RPS; en[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
-                    for (int i0 = tid >> 2; i0 < nn; i0 += RPS * 4) {
+                    for (int u = 0; u < 4; u++) { int i = (tid >> sh) + u * RPS; en[u] = (i < nn) ? src[start + i] : 0xffffffffu; }
+                    for (int i0 = tid >> sh; i0 < nn; i0 += RPS * 4) {
                         uint32_t e[4]; float4 v[4];
 #pragma unroll
                         for (int u = 0; u < 4; u++) e[u] = en[u];
@@ -250,12 +255,15 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_random(F16FitParams P) {
                             if (e[u] != 0xffffffffu && x <= tk) acc += 1ull | ((unsigned long long)f16_y(e[u]) << 32);
                         }
                     }
+                    // lanes with the same tr hold the same candidate: reduce over the others
+                    if (sh < 1) acc += __shfl_xor_sync(F16_FULL, acc, 1);
+                    if (sh < 2) acc += __shfl_xor_sync(F16_FULL, acc, 2);
                     acc += __shfl_xor_sync(F16_FULL, acc, 4);
                     acc += __shfl_xor_sync(F16_FULL, acc, 8);
                     acc += __shfl_xor_sync(F16_FULL, acc, 16);
-                    if (lane < 4) s_part[warp][lane] = acc;
+                    if (lane < (1 << sh)) s_part[warp][lane] = acc;
                     __syncthreads();
-                    if (rtid < 4 && k0 + rtid < ncand) {
+                    if (rtid < (1 << sh) && k0 + rtid < ncand) {
                         unsigned long long s = 0;
                         for (int q2 = 0; q2 < NW; q2++) s += s_part[q2][rtid];
                         s_cnt[k0 + rtid] = s;

@@ -11,14 +11,15 @@ from flake16_framework_b200 import ops, synth, hostprep as hp
 kinds = (sys.argv[1] if len(sys.argv) > 1 else "ET").split(",")
 nts = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "100,1600").split(",")]
 parsed = hp.tests_to_arrays(synth.make_tests_dict(100000, 16))
-X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY, hp.FEATURE_SETS["Flake16"])
-X = np.ascontiguousarray(hp.preprocess(X, "Scaling")); d = 16
+fsname = sys.argv[3] if len(sys.argv) > 3 else "Flake16"
+X, y, _ = hp.feat_lab_proj(parsed, hp.FLAKY, hp.FEATURE_SETS[fsname])
+X = np.ascontiguousarray(hp.preprocess(X, "Scaling")); d = X.shape[1]
 tr, te = next(iter(hp.kfold_split(hp.stratified_kfold_test_folds(y))))
 Xd = torch.from_numpy(X).cuda(); yd = torch.from_numpy(y.astype(np.uint8)).cuda()
 tri = torch.from_numpy(tr).cuda()
 Xrow = ops.rows_f32(Xd, tri); ytr = ops.gather_u8(yd, tri)
 sidx = ops.argsort_columns(Xrow, d)
-out = [os.path.basename(os.environ.get("F16_LIB", "main")) + (" ET_WARP" if os.environ.get("F16_ET_WARP") else "")]
+out = [os.path.basename(os.environ.get("F16_LIB", "main")) + " " + fsname]
 for kind in kinds:
     for nt in nts:
         best, dig = 1e9, ""
