@@ -377,3 +377,28 @@ def test_native_tests_json_parser_equals_json_module(tmp_path):
     json.dump({"p\\q": {"a": [0, 1, 2.0]}}, open(e, "w"))
     assert hp._parse_tests_native(e) is None
     assert list(hp.parse_tests(e)[2]) == ["p\\q"]
+
+
+def test_node_capacity_bookkeeping_and_bench_config_selectors():
+    """The grid engine's learnt node capacities (first fit of a key: worst case; later: 1.5 x the
+    largest ratio seen + 1024, never above 2n - 1; disabled instances always ask for the worst case)
+    and bench.py's BASELINE config selectors."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from flake16_framework_b200 import scores as S
+    S._NodeCaps._seen.clear()
+    caps = S._NodeCaps()
+    key = ("NOD", "Flake16", "None", "SMOTE", "Extra Trees", 18)
+    assert caps.cap(key, 178200) == 0                       # unknown: f16_forest_fit_cap takes 0 as "2n - 1"
+    caps.update(key, 178200, 16000)
+    caps.update(key, 178200, 15000)                         # the largest ratio is kept
+    assert caps.cap(key, 178200) == int(1.5 * (16000 / 178200) * 178200) + 1024
+    assert caps.cap(key, 100) == 2 * 100 - 1                # never above the worst case
+    assert S._NodeCaps().cap(key, 178200) > 0               # a later run starts from what was learnt
+    assert S._NodeCaps(enabled=False).cap(key, 178200) == 0
+    S._NodeCaps._seen.clear()
+    allc = S.all_config_keys()
+    assert len(bench.select_configs(allc, "grid216")) == 216 and len(bench.select_configs(allc, "slice")) == 18
+    assert bench.select_configs(allc, "config2") == [("NOD", "Flake16", "None", "None", "Random Forest")]
+    assert len(bench.select_configs(allc, "config3")) == 2 and len(bench.select_configs(allc, "config5")) == 12
+    assert all(c[3] == "SMOTE ENN" and c[4] == "Extra Trees" for c in bench.select_configs(allc, "config5"))
