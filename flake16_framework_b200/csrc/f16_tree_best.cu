@@ -91,6 +91,9 @@ int f16_launch_bootstrap(const uint32_t* seeds_dev, int n_trees, int n, uint32_t
 #ifndef F16_WPU
 #define F16_WPU 8             // 32-entry tiles per round of the list partition (this many loads in flight + as many prefetched)
 #endif
+#ifndef F16_MAX_SEG
+#define F16_MAX_SEG 8            // most warps that share one evaluated feature's scan
+#endif
 #ifndef F16_SPLIT_SCAN
 #define F16_SPLIT_SCAN 1     // two warps per evaluated feature when the CTA has them (see the candidate scan)
 #endif
@@ -360,39 +363,56 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
             BestCand best;
             best.proxy = -INFINITY; best.key = ~0ull; best.v_prev = 0.f; best.v = 0.f; best.l0 = 0; best.l1 = 0;
             const int t0 = c.c0, t1 = c.c1;
-            const bool split_scan = F16_SPLIT_SCAN && (2 * n_eval <= NW);
-            const int n_scan = split_scan ? 2 * n_eval : n_eval;
+            // SEG warps per evaluated feature (a power of two, NW / n_eval rounded down, at most 8): half of
+            // them walk segments of the first half of the slice upwards, half walk segments of the second
+            // half downwards.  A segment that does not start at an end of the slice first sums the class
+            // weights that precede it (coalesced entry loads, no value gathers) - its prefix offset.
+            int seg = 1;
+            if (F16_SPLIT_SCAN && n_eval > 0) { while (seg < F16_MAX_SEG && 2 * seg * n_eval <= NW) seg <<= 1; }
+            const bool split_scan = seg > 1;
+            const int segh = seg >> 1;                           // segments per direction
+            const int n_scan = n_eval * seg;
             for (int wk = warp; wk < n_scan; wk += NW) {
-                const int k = split_scan ? (wk >> 1) : wk;
-                const bool rev = split_scan && (wk & 1);
+                const int k = split_scan ? (wk / seg) : wk;
+                const int sidx = split_scan ? (wk % seg) : 0;
+                const bool rev = split_scan && (sidx >= segh);
                 const int h = split_scan ? (nn + 1) / 2 : nn;   // upwards: positions [1, h); downwards: [h, nn)
                 const int f = s_eval_f[k];
                 const uint32_t* o = src + (size_t)f * stride + start;
                 unsigned long long carry = 0;
                 if (!rev) {
+                    // this warp's segment of the upward half: entries [lo, hi)
+                    const int lo = split_scan ? (int)((long long)sidx * h / segh) : 0;
+                    const int hi = split_scan ? (int)((long long)(sidx + 1) * h / segh) : nn;
                     float prev_last = 0.f;
+                    if (lo > 0) {
+                        unsigned long long pre = 0;
+                        for (int p = lane; p < lo; p += 32) { const uint32_t e = o[p]; pre += (unsigned long long)f16_w(e) << (f16_y(e) ? 32 : 0); }
+                        carry = f16_warp_sum_u64(pre);
+                        prev_last = value(o[lo - 1], f);
+                    }
                     // 4 consecutive entries per lane: one warp scan per 128 entries; the entries of the
                     // NEXT round are loaded while this round's value gathers are in flight (entry ->
                     // value is a chain of two memory latencies; overlapped, a round costs one)
                     uint32_t en[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) en[j] = (lane * 4 + j < h) ? o[lane * 4 + j] : 0u;
-                    for (int base = 0; base < h; base += 128) {
+                    for (int j = 0; j < 4; j++) en[j] = (lo + lane * 4 + j < hi) ? o[lo + lane * 4 + j] : 0u;
+                    for (int base = lo; base < hi; base += 128) {
                         const int p0 = base + lane * 4;
                         uint32_t e[4]; float v[4]; unsigned long long my[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) e[j] = en[j];
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            v[j] = (p0 + j < h) ? value(e[j], f) : INFINITY;
-                        if (base + 128 < h) {
+                            v[j] = (p0 + j < hi) ? value(e[j], f) : INFINITY;
+                        if (base + 128 < hi) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) en[j] = (p0 + 128 + j < h) ? o[p0 + 128 + j] : 0u;
+                            for (int j = 0; j < 4; j++) en[j] = (p0 + 128 + j < hi) ? o[p0 + 128 + j] : 0u;
                         }
                         unsigned long long run = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            my[j] = (p0 + j < h) ? ((unsigned long long)f16_w(e[j]) << (f16_y(e[j]) ? 32 : 0)) : 0ull;
+                            my[j] = (p0 + j < hi) ? ((unsigned long long)f16_w(e[j]) << (f16_y(e[j]) ? 32 : 0)) : 0ull;
                             run += my[j];
                         }
                         unsigned long long incl = f16_warp_incl_scan_u64(run);
@@ -402,7 +422,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const int p = p0 + j;
-                            if (p < h && p > 0 && v[j] > __fadd_rn(vp, 1e-7f)) {
+                            if (p < hi && p > 0 && v[j] > __fadd_rn(vp, 1e-7f)) {
                                 int l0 = (int)(uint32_t)ex, l1 = (int)(ex >> 32);
                                 double proxy = gini_proxy(l0, l1, t0, t1);
                                 if (proxy > best.proxy) {
@@ -420,13 +440,21 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                     // RIGHT sum of candidate position q (rows q .. nn-1); the candidate test compares
                     // entry q with entry q - 1 = reversed element i + 1 (the lane's next element, the
                     // next lane's first one, or - for lane 31 - one extra load)
-                    const int m = nn - h;                  // candidate positions h .. nn-1
+                    const int m = nn - h;                  // candidate positions h .. nn-1 = reversed elements 0 .. m-1
+                    // this warp's segment of the downward half: reversed elements [i_lo, i_hi)
+                    const int rs = sidx - segh;
+                    const int i_lo = (int)((long long)rs * m / segh), i_hi = (int)((long long)(rs + 1) * m / segh);
+                    if (i_lo > 0) {
+                        unsigned long long pre = 0;
+                        for (int i = lane; i < i_lo; i += 32) { const uint32_t e = o[nn - 1 - i]; pre += (unsigned long long)f16_w(e) << (f16_y(e) ? 32 : 0); }
+                        carry = f16_warp_sum_u64(pre);
+                    }
                     // element m (entry h - 1) is loaded for its value only
                     uint32_t en[4], en_after;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) en[j] = (lane * 4 + j <= m) ? o[nn - 1 - (lane * 4 + j)] : 0u;
-                    en_after = (lane == 31 && lane * 4 + 4 <= m) ? o[nn - 1 - (lane * 4 + 4)] : 0u;
-                    for (int base = 0; base < m; base += 128) {
+                    for (int j = 0; j < 4; j++) en[j] = (i_lo + lane * 4 + j <= m) ? o[nn - 1 - (i_lo + lane * 4 + j)] : 0u;
+                    en_after = (lane == 31 && i_lo + lane * 4 + 4 <= m) ? o[nn - 1 - (i_lo + lane * 4 + 4)] : 0u;
+                    for (int base = i_lo; base < i_hi; base += 128) {
                         const int i0 = base + lane * 4;
                         uint32_t e[4]; float v[4]; unsigned long long my[4];
 #pragma unroll
@@ -436,7 +464,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                         for (int j = 0; j < 4; j++)
                             v[j] = (i0 + j <= m) ? value(e[j], f) : -INFINITY;
                         float v_after = (lane == 31 && i0 + 4 <= m) ? value(e_after, f) : -INFINITY;
-                        if (base + 128 < m) {
+                        if (base + 128 < i_hi) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) en[j] = (i0 + 128 + j <= m) ? o[nn - 1 - (i0 + 128 + j)] : 0u;
                             en_after = (lane == 31 && i0 + 132 <= m) ? o[nn - 1 - (i0 + 132)] : 0u;
@@ -455,7 +483,7 @@ __global__ void __launch_bounds__(NT, F16_MINB) k_build_best(F16FitParams P) {
                         for (int j = 0; j < 4; j++) {
                             r += my[j];
                             const float vn = (j < 3) ? v[j < 3 ? j + 1 : 3] : v_after;     // entry q - 1
-                            if (i0 + j < m && v[j] > __fadd_rn(vn, 1e-7f)) {
+                            if (i0 + j < i_hi && v[j] > __fadd_rn(vn, 1e-7f)) {
                                 const int q = nn - 1 - (i0 + j);
                                 int l0 = t0 - (int)(uint32_t)r, l1 = t1 - (int)(r >> 32);
                                 double proxy = gini_proxy(l0, l1, t0, t1);
