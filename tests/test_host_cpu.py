@@ -402,3 +402,27 @@ def test_node_capacity_bookkeeping_and_bench_config_selectors():
     assert bench.select_configs(allc, "config2") == [("NOD", "Flake16", "None", "None", "Random Forest")]
     assert len(bench.select_configs(allc, "config3")) == 2 and len(bench.select_configs(allc, "config5")) == 12
     assert all(c[3] == "SMOTE ENN" and c[4] == "Extra Trees" for c in bench.select_configs(allc, "config5"))
+
+
+def test_native_parser_number_round_trip_random(tmp_path):
+    """20 000 random doubles (all exponents, subnormals, integers up to 2**63) written the way
+    json.dump writes them come back from the library's scanner with the bit patterns json.load gives."""
+    from flake16_framework_b200 import hostprep as hp
+    rs = np.random.RandomState(7)
+    bits = rs.randint(0, 2 ** 63, size=12000, dtype=np.int64).astype(np.uint64) | (rs.randint(0, 2, 12000).astype(np.uint64) << np.uint64(63))
+    vals = bits.view(np.float64)
+    vals = vals[np.isfinite(vals)]
+    ints = [int(v) for v in rs.randint(-2 ** 62, 2 ** 62, size=4000)] + [2 ** 53 + 1, 2 ** 63 - 1, -(2 ** 63) + 1, 10 ** 18, 10 ** 19]
+    smalls = [float(v) for v in rs.randn(4000)] + [5e-324, 2.2250738585072009e-308, 1.7976931348623157e308, 0.1, 1e23]
+    nums = [float(v) for v in vals] + ints + smalls
+    rs.shuffle(nums)
+    rows = {}
+    width = 18
+    for i in range(0, len(nums) - width, width - 2):
+        rows["t%d" % i] = [0, 1] + nums[i:i + width - 2]
+    p = str(tmp_path / "rand.json")
+    json.dump({"p": rows}, open(p, "w"), indent=4)
+    a = hp._parse_tests_native(p)
+    b = hp.tests_to_arrays(json.load(open(p)))
+    assert a is not None
+    assert np.array_equal(a[0].view(np.int64), np.asarray(b[0], dtype=np.float64).view(np.int64))
